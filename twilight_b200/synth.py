@@ -1,0 +1,160 @@
+"""Seeded synthetic inputs of the shapes BASELINE.json names: sequences evolved along a random binary
+guide tree with substitutions and short indels. Pure numpy; used by tests and by bench.py (data = "synthetic").
+
+Tree representation: `Tree(parent, children, blen, names)` with integer node ids, leaves are 0..n_leaves-1.
+"""
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+NT = np.frombuffer(b"ACGT", dtype=np.uint8)
+RNA = np.frombuffer(b"ACGU", dtype=np.uint8)
+AA = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", dtype=np.uint8)
+# Robinson-Robinson background frequencies, order ACDEFGHIKLMNPQRSTVWY
+AA_FREQ = np.array([0.0780, 0.0192, 0.0536, 0.0630, 0.0386, 0.0738, 0.0220, 0.0514, 0.0574, 0.0902, 0.0224, 0.0449,
+                    0.0520, 0.0426, 0.0513, 0.0712, 0.0584, 0.0644, 0.0133, 0.0321])
+
+
+@dataclass
+class Tree:
+    n_leaves: int
+    parent: np.ndarray                      # [n_nodes] int32, -1 at the root
+    children: List[List[int]]
+    blen: np.ndarray                        # [n_nodes] float32 branch length to the parent
+    root: int
+    names: List[str] = field(default_factory=list)
+
+    @property
+    def n_nodes(self):
+        return len(self.parent)
+
+    def newick(self) -> str:
+        out = {}
+        order = self.postorder()
+        for v in order:
+            if not self.children[v]:
+                out[v] = f"{self.names[v]}:{self.blen[v]:.6f}"
+            else:
+                inner = ",".join(out.pop(c) for c in self.children[v])
+                out[v] = f"({inner}):{self.blen[v]:.6f}" if v != self.root else f"({inner});"
+        return out[self.root]
+
+    def postorder(self) -> List[int]:
+        order, stack = [], [(self.root, False)]
+        while stack:
+            v, done = stack.pop()
+            if done:
+                order.append(v)
+            else:
+                stack.append((v, True))
+                for c in reversed(self.children[v]):
+                    stack.append((c, False))
+        return order
+
+
+def random_tree(n_leaves: int, seed: int = 0, shape: str = "yule", mean_blen: float = 0.05) -> Tree:
+    """Random rooted binary tree. shape: 'yule' (random joins, RNASim-like depth), 'balanced', 'caterpillar'."""
+    rng = np.random.default_rng(seed)
+    n_nodes = 2 * n_leaves - 1
+    parent = np.full(n_nodes, -1, np.int32)
+    children: List[List[int]] = [[] for _ in range(n_nodes)]
+    nxt = n_leaves
+    if shape == "balanced":
+        layer = list(range(n_leaves))
+        while len(layer) > 1:
+            up = []
+            for a in range(0, len(layer) - 1, 2):
+                children[nxt] = [layer[a], layer[a + 1]]
+                parent[layer[a]] = parent[layer[a + 1]] = nxt
+                up.append(nxt)
+                nxt += 1
+            if len(layer) % 2:
+                up.append(layer[-1])
+            layer = up
+    elif shape == "caterpillar":
+        cur = 0
+        for leaf in range(1, n_leaves):
+            children[nxt] = [cur, leaf]
+            parent[cur] = parent[leaf] = nxt
+            cur = nxt
+            nxt += 1
+    else:
+        live = list(range(n_leaves))
+        while len(live) > 1:
+            a, b = rng.choice(len(live), size=2, replace=False)
+            x, y = live[a], live[b]
+            children[nxt] = [x, y]
+            parent[x] = parent[y] = nxt
+            for idx in sorted((a, b), reverse=True):
+                live.pop(idx)
+            live.append(nxt)
+            nxt += 1
+    root = n_nodes - 1
+    blen = rng.exponential(mean_blen, n_nodes).astype(np.float32) + np.float32(1e-4)
+    blen[root] = 0
+    return Tree(n_leaves, parent, children, blen, root, [f"L{i}" for i in range(n_leaves)])
+
+
+def _mutate(seq: np.ndarray, b: float, rng, alphabet: np.ndarray, indel_rate: float, probs=None) -> np.ndarray:
+    L = len(seq)
+    p_sub = 1.0 - np.exp(-b)
+    hit = rng.random(L) < p_sub
+    if hit.any():
+        seq = seq.copy()
+        seq[hit] = rng.choice(alphabet, size=int(hit.sum()), p=probs)
+    n_ev = rng.poisson(indel_rate * b * L)
+    if n_ev == 0:
+        return seq
+    pos = np.sort(rng.integers(0, max(L, 1), n_ev))
+    parts, last = [], 0
+    for p in pos:
+        if p < last:
+            continue
+        parts.append(seq[last:p])
+        ln = int(rng.geometric(0.4))
+        if rng.random() < 0.5:
+            parts.append(rng.choice(alphabet, size=ln, p=probs))
+            last = p
+        else:
+            last = min(L, p + ln)
+    parts.append(seq[last:])
+    return np.concatenate(parts) if parts else seq
+
+
+def evolve(tree: Tree, root_len: int, seed: int = 0, kind: str = "rna", indel_rate: float = 0.03,
+           n_frac: float = 0.0) -> List[bytes]:
+    """Evolve a random root sequence down the tree; returns the leaf sequences (bytes) in leaf-id order."""
+    rng = np.random.default_rng(seed + 7919)
+    alphabet = {"rna": RNA, "dna": NT, "protein": AA}[kind]
+    probs = AA_FREQ / AA_FREQ.sum() if kind == "protein" else None
+    seqs: List[Optional[np.ndarray]] = [None] * tree.n_nodes
+    seqs[tree.root] = rng.choice(alphabet, size=root_len, p=probs)
+    stack = [tree.root]
+    leaves: List[Optional[bytes]] = [None] * tree.n_leaves
+    while stack:
+        v = stack.pop()
+        s = seqs[v]
+        for c in tree.children[v]:
+            seqs[c] = _mutate(s, float(tree.blen[c]), rng, alphabet, indel_rate, probs)
+            stack.append(c)
+        if not tree.children[v]:
+            if n_frac > 0:
+                s = s.copy()
+                s[rng.random(len(s)) < n_frac] = ord("N")
+            leaves[v] = s.tobytes()
+        seqs[v] = None
+    return leaves  # type: ignore
+
+
+def levels_bottom_up(tree: Tree):
+    """Sibling pairs grouped by level, the schedule of getProgressivePairs mode 0 (progressive.cpp:52-68):
+    level(node) = 1 + max(level(children)) with leaves at 0; returns [[(first_child, second_child, parent), ...], ...]."""
+    lvl = np.zeros(tree.n_nodes, np.int32)
+    out = {}
+    for v in tree.postorder():
+        ch = tree.children[v]
+        if ch:
+            lvl[v] = 1 + max(lvl[c] for c in ch)
+            out.setdefault(int(lvl[v]) - 1, []).append((ch[0], ch[1], v))
+    return [out[k] for k in sorted(out)]
