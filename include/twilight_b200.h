@@ -1,0 +1,107 @@
+/* twilight_b200.h — C ABI of the B200-native TWILIGHT alignment path (libtwilight_b200.so).
+ *
+ * This is the drop-in boundary for the reference's per-level alignment kernel:
+ *   msa::alnFunction                                  (src/msa.hpp:175, invoked at src/progressive.cpp:180)
+ *   cpu::alignmentKernel_CPU / parallelAlignmentCPU   (src/alignment-cpu.cpp:32, 36-183)
+ *   gpu::alignmentKernel_GPU / parallelAlignmentGPU   (src/cuda/alignment-gpu.cu:12, 182-450)
+ * The C++ adapter with the alnFunction signature that a maintainer links into the unchanged host lives in
+ * twilight_b200/host/alignment_b200.cpp; INTEGRATION.md shows the two-line change in twilight-main.cpp.
+ *
+ * Conventions: every function returns 0 on success or a negative TWL_E_* code, never throws, never exits.
+ * A context is bound to one CUDA device and is used from one host thread at a time (as the reference's
+ * per-GPU GPU_pointers object, src/msa.hpp:220). There is NO CPU fallback: without a usable CUDA device
+ * twl_init fails with TWL_E_NO_DEVICE.
+ *
+ * Alignment-path codes (int8): 0 = both advance, 1 = query-only column, 2 = reference-only column (src/msa.hpp:50,
+ * SURVEY.md conventions). "ref" is the first node of a pair, "qry" the second.
+ */
+#ifndef TWILIGHT_B200_H
+#define TWILIGHT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TWL_OK 0
+#define TWL_E_NO_DEVICE (-1)   /* no CUDA device / wrong architecture */
+#define TWL_E_CUDA (-2)        /* a CUDA call failed; see twl_last_error */
+#define TWL_E_ARG (-3)         /* invalid argument */
+#define TWL_E_NOMEM (-4)       /* device or pinned-host allocation failed */
+#define TWL_E_STATE (-5)       /* call order violated (e.g. params not set) */
+
+/* Per-pair status, mirrors Talco_xdrop errorType (src/TALCO-XDrop.cpp:248) */
+#define TWL_ST_OK 0
+#define TWL_ST_XDROP 1         /* band died under the x-drop rule (TALCO-XDrop.cpp:323-329) */
+#define TWL_ST_BAND 2          /* anti-diagonal wider than fLen (TALCO-XDrop.cpp:331-338) */
+#define TWL_ST_FATAL 3         /* index overrun (TALCO-XDrop.cpp:311-318, 658-667) */
+
+typedef struct twl_ctx twl_ctx;
+
+/* ---- lifecycle: replaces Option::getGpuInfo (src/cuda/gpu-info.cu:6-94) and the GPU_pointers
+ *      allocate/free pair (src/cuda/alignment-gpu.cu:18-138) ------------------------------------------------ */
+int twl_device_count(void);
+int twl_init(int device, twl_ctx **out);
+void twl_destroy(twl_ctx *ctx);
+const char *twl_last_error(const twl_ctx *ctx);   /* ctx may be NULL: returns the last init error */
+
+/* ---- scoring parameters: msa::Params (src/msa.hpp:98-109, src/scoring-matrix.cpp:81-137) and the
+ *      Talco_xdrop::Params defaults derived from it (src/TALCO-XDrop.cpp:36-53). M = 5 (nucleotide, profile width
+ *      6) or 21 (protein, profile width 22). score is M*M row-major and is copied. -------------------------- */
+int twl_set_params(twl_ctx *ctx, const float *score, int M, float gap_open, float gap_extend, float gap_boundary);
+/* marker = tile marker (default 1024, TALCO-XDrop.cpp:51); 1 <= marker <= 1024. */
+int twl_set_marker(twl_ctx *ctx, int marker);
+
+/* ---- level batch of profile pairs: the DP + traceback of every pair of one guide-tree level.
+ *      Replaces the Talco_xdrop::Align_freq call of alignment-cpu.cpp:98-107 (and the kernel launch of
+ *      alignment-gpu.cu:294-333). Semantics are those of the reference CPU path (float scores, marker 1024,
+ *      fLen 4096, x-drop 1000*|gapExtend|), not of src/cuda. ------------------------------------------------ */
+typedef struct {
+    const float *freq_ref;      /* [ref_len][P] row-major column profile after gappy-column removal */
+    const float *freq_qry;      /* [qry_len][P] */
+    const float *gap_open_ref;  /* [ref_len] position-specific penalties (calculatePSGP, alignment-helper.cpp:168) */
+    const float *gap_ext_ref;
+    const float *gap_open_qry;  /* [qry_len] */
+    const float *gap_ext_qry;
+    int32_t ref_len, qry_len;   /* both >= 1 */
+    float ref_num, qry_num;     /* sequences per side (denominator, TALCO-XDrop.cpp:269) */
+    float gap_char_score;       /* gapExtend, or 0 for tasks 1/2 and >10000 sequences (alignment-cpu.cpp:88) */
+    int32_t xdrop;              /* <=0: default 1000*|gapExtend| (TALCO-XDrop.cpp:49) */
+    int32_t flen;               /* <=0: default 4096 (TALCO-XDrop.cpp:50) */
+} twl_profile_pair;
+
+typedef struct {
+    int32_t status;             /* TWL_ST_* */
+    int32_t path_len;           /* 0 when status != 0 */
+    int32_t tiles;              /* TALCO tiles executed */
+    int32_t reserved;
+    uint64_t cells;             /* DP cell updates: sum over diagonals of (U-L+1), SURVEY.md §8(d) */
+    uint64_t diagonals;
+} twl_pair_result;
+
+/* One call = host->device copy of the profiles, the DP/traceback kernels, device->host copy of the paths.
+ * paths[p] must hold ref_len+qry_len bytes. */
+int twl_align_profiles(twl_ctx *ctx, const twl_profile_pair *pairs, int n_pairs, int8_t *const *paths,
+                       twl_pair_result *results);
+
+/* The same work split in three so that a caller (bench.py, or a pipeline that overlaps levels) can keep the batch
+ * resident in HBM: stage() packs + uploads, run() launches the kernels on the resident batch (may be called
+ * repeatedly), fetch() downloads paths and results of the last run(). */
+int twl_batch_stage(twl_ctx *ctx, const twl_profile_pair *pairs, int n_pairs);
+int twl_batch_run(twl_ctx *ctx);
+int twl_batch_fetch(twl_ctx *ctx, int8_t *const *paths, twl_pair_result *results);
+
+/* Device time (CUDA events on the context's stream) of the kernels of the last run(), in milliseconds, and the number
+ * of kernel launches it issued. */
+float twl_last_kernel_ms(const twl_ctx *ctx);
+int twl_last_launch_count(const twl_ctx *ctx);
+
+/* Library build information (arch string etc.). */
+const char *twl_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TWILIGHT_B200_H */

@@ -1,0 +1,111 @@
+"""GPU parity of the TALCO-XDrop DP + traceback (C ABI twl_align_profiles) against the CPU oracle.
+
+Bar: bit-exact alignment paths, identical errorType, identical cell / tile / diagonal counts."""
+import numpy as np
+import pytest
+
+from tests import oracle_lib as ol
+from tests.helpers import records_to_pairs, synthetic_records
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # n_leaves, root_len, seed, marker
+    (8, 300, 0, 1024),     # single tile per pair
+    (16, 1500, 1, 1024),   # RNASim-shaped, 2-4 tiles per pair
+    (12, 700, 2, 128),     # small marker: many tiles, convergence logic on every tile
+    (6, 4000, 3, 256),
+    (10, 900, 4, 64),
+    (5, 2600, 5, 1024),
+]
+
+
+@pytest.fixture(scope="module")
+def ctxs():
+    import twilight_b200
+    cache = {}
+
+    def get(marker):
+        if marker not in cache:
+            cache[marker] = twilight_b200.Context(marker=marker)
+        return cache[marker]
+    yield get
+    for c in cache.values():
+        c.close()
+
+
+@pytest.mark.parametrize("n,L,seed,marker", CASES)
+def test_paths_match_port(ctxs, n, L, seed, marker):
+    cfg, _, _, _, recs = synthetic_records(n, L, seed, marker)
+    ctx = ctxs(marker)
+    outs = ctx.align_profiles(records_to_pairs(recs, cfg))
+    assert len(outs) == len(recs)
+    for k, (o, r) in enumerate(zip(outs, recs)):
+        assert o.status == r.error == 0, f"pair {k}: status {o.status} vs {r.error}"
+        assert o.tiles == r.tiles, f"pair {k}: tiles {o.tiles} vs {r.tiles}"
+        assert o.cells == r.cells, f"pair {k}: cells {o.cells} vs {r.cells}"
+        assert len(o.path) == len(r.aln_wo), f"pair {k}: path length {len(o.path)} vs {len(r.aln_wo)}"
+        assert np.array_equal(o.path, r.aln_wo), f"pair {k}: first diff at {int(np.argmax(o.path != r.aln_wo))}"
+
+
+def test_paths_match_reference_build(ctxs):
+    if not ol.have_ref():
+        pytest.skip("oracle/_ref/libtalco_ref.so not built")
+    cfg, _, _, _, recs = synthetic_records(10, 1200, 11, 256)
+    outs = ctxs(256).align_profiles(records_to_pairs(recs, cfg))
+    for o, r in zip(outs, recs):
+        a, e = ol.ref_talco(cfg, r.profile[0], r.profile[1], r.gap_op[0], r.gap_ex[0], r.gap_op[1], r.gap_ex[1], r.ref.aln_num, r.qry.aln_num)
+        assert o.status == e
+        assert np.array_equal(o.path, a)
+
+
+def test_error_codes(ctxs):
+    """errorType 1 (band dies) and 2 (band wider than fLen) must come back exactly as the reference reports them."""
+    import twilight_b200
+    rng = np.random.default_rng(5)
+    cfg, _, _, _, recs = synthetic_records(4, 600, 7, 1024)
+    r = recs[-1]
+    ctx = ctxs(1024)
+    for xdrop, flen in ((5, 4096), (5000, 8), (40, 4096), (5000, 40)):
+        c = ol.TalcoCfg(xdrop=xdrop, flen=flen)
+        want, err, cells, tiles, _ = ol.port_talco(c, r.profile[0], r.profile[1], r.gap_op[0], r.gap_ex[0], r.gap_op[1], r.gap_ex[1], r.ref.aln_num, r.qry.aln_num)
+        pair = twilight_b200.ProfilePairIn(r.profile[0], r.profile[1], r.gap_op[0], r.gap_ex[0], r.gap_op[1], r.gap_ex[1],
+                                           r.ref.aln_num, r.qry.aln_num, xdrop=xdrop, flen=flen)
+        out = ctx.align_profiles([pair])[0]
+        assert out.status == err, (xdrop, flen, out.status, err)
+        assert np.array_equal(out.path, want)
+
+
+def test_wide_band_goes_through_global_state(ctxs):
+    """A huge x-drop keeps the whole matrix alive: bands wider than the shared-memory capacity are re-run by the wide
+    variant and must still match."""
+    import twilight_b200
+    cfg, _, _, _, recs = synthetic_records(2, 1800, 9, 1024)
+    r = recs[0]
+    c = ol.TalcoCfg(xdrop=2000000)
+    want, err, cells, tiles, _ = ol.port_talco(c, r.profile[0], r.profile[1], r.gap_op[0], r.gap_ex[0], r.gap_op[1], r.gap_ex[1], 1, 1)
+    pair = twilight_b200.ProfilePairIn(r.profile[0], r.profile[1], r.gap_op[0], r.gap_ex[0], r.gap_op[1], r.gap_ex[1], 1, 1, xdrop=2000000)
+    out = ctxs(1024).align_profiles([pair])[0]
+    assert out.status == err == 0
+    assert out.cells == cells
+    assert np.array_equal(out.path, want)
+
+
+def test_empty_batch_and_tiny_pairs(ctxs):
+    import twilight_b200
+    ctx = ctxs(1024)
+    assert ctx.align_profiles([]) == []
+    cfg = ol.TalcoCfg()
+    rng = np.random.default_rng(3)
+    pairs, wants = [], []
+    for (R, Q) in ((1, 1), (1, 5), (5, 1), (2, 2), (3, 40), (40, 3)):
+        fr = np.zeros((R, 6), np.float32); fr[np.arange(R), rng.integers(0, 4, R)] = 1
+        fq = np.zeros((Q, 6), np.float32); fq[np.arange(Q), rng.integers(0, 4, Q)] = 1
+        go_r = np.full(R, -50, np.float32); ge_r = np.full(R, -5, np.float32)
+        go_q = np.full(Q, -50, np.float32); ge_q = np.full(Q, -5, np.float32)
+        wants.append(ol.port_talco(cfg, fr, fq, go_r, ge_r, go_q, ge_q, 1, 1))
+        pairs.append(twilight_b200.ProfilePairIn(fr, fq, go_r, ge_r, go_q, ge_q, 1, 1))
+    outs = ctx.align_profiles(pairs)
+    for o, w in zip(outs, wants):
+        assert o.status == w[1]
+        assert np.array_equal(o.path, w[0])

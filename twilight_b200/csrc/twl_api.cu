@@ -1,0 +1,400 @@
+// twl_api.cu — host side of the C ABI declared in include/twilight_b200.h: context lifecycle, batch staging in
+// pinned memory, kernel launches on one stream, result download. No CPU alignment code lives here: if CUDA is not
+// usable every entry point fails.
+#include "../../include/twilight_b200.h"
+#include "twl_device.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace twl {
+size_t genericStateWords(int stateCap);
+cudaError_t launchTalcoGeneric(int P, bool globalState, const TalcoArgs &args, int grid, size_t dynSmemBytes, cudaStream_t stream);
+int genericThreads();
+} // namespace twl
+
+namespace {
+
+std::string g_initError;
+
+template <typename T>
+struct DevBuf {
+    T *ptr = nullptr;
+    size_t cap = 0; // elements
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        size_t want = n + n / 4 + 256;
+        cudaError_t e = cudaMalloc(&ptr, want * sizeof(T));
+        if (e != cudaSuccess) { e = cudaMalloc(&ptr, n * sizeof(T)); want = n; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
+};
+
+template <typename T>
+struct PinBuf {
+    T *ptr = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (ptr) cudaFreeHost(ptr);
+        ptr = nullptr;
+        cap = 0;
+        size_t want = n + n / 4 + 256;
+        cudaError_t e = cudaMallocHost(&ptr, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (ptr) cudaFreeHost(ptr); ptr = nullptr; cap = 0; }
+};
+
+} // namespace
+
+struct twl_ctx {
+    int device = 0;
+    int smCount = 0;
+    cudaStream_t stream = nullptr;
+    bool ownStream = true;
+    cudaEvent_t evStart = nullptr, evStop = nullptr;
+    std::string error;
+
+    // scoring
+    int M = 0, P = 0;
+    float gapOpen = 0, gapExtend = 0, gapBoundary = 0;
+    int marker = twl::kMaxMarker;
+    DevBuf<float> dScore;
+
+    // staged batch
+    int nPairs = 0;
+    bool staged = false, ran = false;
+    size_t profWords = 0, pathBytes = 0;
+    std::vector<twl::DevPair> hPairs;
+    std::vector<int> hOrder;
+    int maxFLen = 0;
+    PinBuf<float> hProf;
+    PinBuf<int8_t> hPaths;
+    PinBuf<twl::DevResult> hResults;
+    DevBuf<float> dProf;
+    DevBuf<twl::DevPair> dPairs;
+    DevBuf<twl::DevResult> dResults;
+    DevBuf<int8_t> dPaths;
+    DevBuf<int> dOrder, dOverflow;
+    DevBuf<int> dCounters; // [0] queue A, [1] nWork A, [2] queue B, [3] overflow count (= nWork B)
+    DevBuf<uint8_t> dTb;
+    DevBuf<float> dState;
+
+    float lastMs = -1.0f;
+    int lastLaunches = 0;
+    bool timingPending = false;
+};
+
+namespace {
+
+int fail(twl_ctx *ctx, int code, const std::string &msg) {
+    if (ctx) ctx->error = msg;
+    else g_initError = msg;
+    return code;
+}
+
+#define TWL_CUDA(ctx, call)                                                                             \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            return fail(ctx, (e_ == cudaErrorMemoryAllocation) ? TWL_E_NOMEM : TWL_E_CUDA,              \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                            \
+        }                                                                                               \
+    } while (0)
+
+constexpr int kSmemStateCap = 1020;   // band cells held in shared memory by the narrow generic variant
+constexpr int kNarrowCtasPerSm = 3;
+
+size_t tbBytesPerCta(int marker) {
+    // diagonal k <= marker stores at most k+1 traceback bytes
+    size_t n = static_cast<size_t>(marker + 1) * (marker + 2) / 2;
+    return (n + 255) & ~static_cast<size_t>(255);
+}
+
+void packColumns(float *dst, const float *freq, const float *gapOp, const float *gapEx, int len, int P) {
+    const int PW = P + 2;
+    for (int c = 0; c < len; ++c) {
+        float *d = dst + static_cast<size_t>(c) * PW;
+        std::memcpy(d, freq + static_cast<size_t>(c) * P, sizeof(float) * P);
+        d[P] = gapOp[c];
+        d[P + 1] = gapEx[c];
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+const char *twl_version(void) { return "twilight_b200 0.1 (sm_100a)"; }
+
+int twl_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int twl_init(int device, twl_ctx **out) {
+    if (!out) return fail(nullptr, TWL_E_ARG, "twl_init: out is null");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, TWL_E_NO_DEVICE, std::string("twl_init: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU fallback");
+    if (device < 0 || device >= n) return fail(nullptr, TWL_E_ARG, "twl_init: device index out of range");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, TWL_E_CUDA, "twl_init: cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return fail(nullptr, TWL_E_NO_DEVICE, "twl_init: device is not sm_100 (kernels are built for sm_100a only)");
+    twl_ctx *ctx = new twl_ctx();
+    ctx->device = device;
+    ctx->smCount = prop.multiProcessorCount;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->evStart) != cudaSuccess || cudaEventCreate(&ctx->evStop) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, TWL_E_CUDA, "twl_init: stream/event creation failed");
+    }
+    *out = ctx;
+    return TWL_OK;
+}
+
+void twl_destroy(twl_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->dScore.release(); ctx->dProf.release(); ctx->dPairs.release(); ctx->dResults.release(); ctx->dPaths.release();
+    ctx->dOrder.release(); ctx->dOverflow.release(); ctx->dCounters.release(); ctx->dTb.release(); ctx->dState.release();
+    ctx->hProf.release(); ctx->hPaths.release(); ctx->hResults.release();
+    if (ctx->evStart) cudaEventDestroy(ctx->evStart);
+    if (ctx->evStop) cudaEventDestroy(ctx->evStop);
+    if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *twl_last_error(const twl_ctx *ctx) { return ctx ? ctx->error.c_str() : g_initError.c_str(); }
+
+int twl_set_params(twl_ctx *ctx, const float *score, int M, float gap_open, float gap_extend, float gap_boundary) {
+    if (!ctx) return TWL_E_ARG;
+    if (!score || (M != 5 && M != 21)) return fail(ctx, TWL_E_ARG, "twl_set_params: M must be 5 (nucleotide) or 21 (protein)");
+    cudaSetDevice(ctx->device);
+    TWL_CUDA(ctx, ctx->dScore.reserve(static_cast<size_t>(M) * M));
+    TWL_CUDA(ctx, cudaMemcpyAsync(ctx->dScore.ptr, score, sizeof(float) * M * M, cudaMemcpyHostToDevice, ctx->stream));
+    TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->M = M;
+    ctx->P = M + 1;
+    ctx->gapOpen = gap_open;
+    ctx->gapExtend = gap_extend;
+    ctx->gapBoundary = gap_boundary;
+    ctx->staged = false;
+    return TWL_OK;
+}
+
+int twl_set_marker(twl_ctx *ctx, int marker) {
+    if (!ctx) return TWL_E_ARG;
+    if (marker < 1 || marker > twl::kMaxMarker) return fail(ctx, TWL_E_ARG, "twl_set_marker: marker must be in [1, 1024]");
+    ctx->marker = marker;
+    return TWL_OK;
+}
+
+int twl_batch_stage(twl_ctx *ctx, const twl_profile_pair *pairs, int n_pairs) {
+    if (!ctx) return TWL_E_ARG;
+    if (ctx->P == 0) return fail(ctx, TWL_E_STATE, "twl_batch_stage: call twl_set_params first");
+    if (n_pairs < 0 || (n_pairs > 0 && !pairs)) return fail(ctx, TWL_E_ARG, "twl_batch_stage: bad pair list");
+    cudaSetDevice(ctx->device);
+    ctx->staged = false;
+    ctx->ran = false;
+    ctx->nPairs = n_pairs;
+    if (n_pairs == 0) { ctx->staged = true; return TWL_OK; }
+    const int P = ctx->P, PW = P + 2;
+    const int defXdrop = static_cast<int>(1000 * -1 * ctx->gapExtend);     // TALCO-XDrop.cpp:49
+    ctx->hPairs.resize(n_pairs);
+    size_t words = 0, bytes = 0;
+    int maxF = 0;
+    for (int p = 0; p < n_pairs; ++p) {
+        const twl_profile_pair &in = pairs[p];
+        if (in.ref_len < 1 || in.qry_len < 1 || !in.freq_ref || !in.freq_qry || !in.gap_open_ref || !in.gap_ext_ref ||
+            !in.gap_open_qry || !in.gap_ext_qry)
+            return fail(ctx, TWL_E_ARG, "twl_batch_stage: pair " + std::to_string(p) + " has empty profiles or null pointers");
+        twl::DevPair &d = ctx->hPairs[p];
+        d.refOff = static_cast<long long>(words); words += static_cast<size_t>(in.ref_len) * PW;
+        d.qryOff = static_cast<long long>(words); words += static_cast<size_t>(in.qry_len) * PW;
+        d.alnOff = static_cast<long long>(bytes); bytes += (static_cast<size_t>(in.ref_len) + in.qry_len + 15) & ~static_cast<size_t>(15);
+        d.refLen = in.ref_len; d.qryLen = in.qry_len;
+        d.refNum = in.ref_num; d.qryNum = in.qry_num;
+        d.gapChar = in.gap_char_score;
+        d.xdrop = in.xdrop > 0 ? in.xdrop : defXdrop;
+        d.fLen = in.flen > 0 ? in.flen : 4096;                             // TALCO-XDrop.cpp:50
+        d.pad = 0;
+        maxF = std::max(maxF, std::min(d.fLen, std::min(d.refLen, d.qryLen)));
+    }
+    ctx->profWords = words;
+    ctx->pathBytes = bytes;
+    ctx->maxFLen = maxF;
+    TWL_CUDA(ctx, ctx->hProf.reserve(words));
+    // pack into pinned memory (memory-bound; a few host threads for big batches)
+    {
+        const int nThreads = (words > (1u << 22)) ? std::min(8u, std::max(1u, std::thread::hardware_concurrency())) : 1;
+        auto work = [&](int t) {
+            for (int p = t; p < n_pairs; p += nThreads) {
+                const twl_profile_pair &in = pairs[p];
+                packColumns(ctx->hProf.ptr + ctx->hPairs[p].refOff, in.freq_ref, in.gap_open_ref, in.gap_ext_ref, in.ref_len, P);
+                packColumns(ctx->hProf.ptr + ctx->hPairs[p].qryOff, in.freq_qry, in.gap_open_qry, in.gap_ext_qry, in.qry_len, P);
+            }
+        };
+        if (nThreads == 1) work(0);
+        else {
+            std::vector<std::thread> pool;
+            for (int t = 1; t < nThreads; ++t) pool.emplace_back(work, t);
+            work(0);
+            for (auto &th : pool) th.join();
+        }
+    }
+    // heaviest pairs first (anti-diagonal count is the serial length of a pair)
+    ctx->hOrder.resize(n_pairs);
+    std::iota(ctx->hOrder.begin(), ctx->hOrder.end(), 0);
+    std::stable_sort(ctx->hOrder.begin(), ctx->hOrder.end(), [&](int x, int y) {
+        return ctx->hPairs[x].refLen + ctx->hPairs[x].qryLen > ctx->hPairs[y].refLen + ctx->hPairs[y].qryLen;
+    });
+
+    TWL_CUDA(ctx, ctx->dProf.reserve(words));
+    TWL_CUDA(ctx, ctx->dPairs.reserve(n_pairs));
+    TWL_CUDA(ctx, ctx->dResults.reserve(n_pairs));
+    TWL_CUDA(ctx, ctx->dPaths.reserve(bytes));
+    TWL_CUDA(ctx, ctx->dOrder.reserve(n_pairs));
+    TWL_CUDA(ctx, ctx->dOverflow.reserve(n_pairs));
+    TWL_CUDA(ctx, ctx->dCounters.reserve(8));
+    TWL_CUDA(ctx, cudaMemcpyAsync(ctx->dProf.ptr, ctx->hProf.ptr, words * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    TWL_CUDA(ctx, cudaMemcpyAsync(ctx->dPairs.ptr, ctx->hPairs.data(), n_pairs * sizeof(twl::DevPair), cudaMemcpyHostToDevice, ctx->stream));
+    TWL_CUDA(ctx, cudaMemcpyAsync(ctx->dOrder.ptr, ctx->hOrder.data(), n_pairs * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // hPairs/hOrder are pageable
+    ctx->staged = true;
+    return TWL_OK;
+}
+
+int twl_batch_run(twl_ctx *ctx) {
+    if (!ctx) return TWL_E_ARG;
+    if (!ctx->staged) return fail(ctx, TWL_E_STATE, "twl_batch_run: no staged batch");
+    cudaSetDevice(ctx->device);
+    ctx->lastLaunches = 0;
+    ctx->lastMs = 0.0f;
+    ctx->timingPending = false;
+    if (ctx->nPairs == 0) { ctx->ran = true; return TWL_OK; }
+    const int n = ctx->nPairs;
+    const int gridA = std::min(n, ctx->smCount * kNarrowCtasPerSm);
+    const int gridB = std::min(n, ctx->smCount);
+    const int wideCap = std::max(ctx->maxFLen, 8);
+    const bool needWide = wideCap > kSmemStateCap;
+    const size_t tbStride = tbBytesPerCta(ctx->marker);
+    const size_t stateStride = twl::genericStateWords(wideCap);
+    TWL_CUDA(ctx, ctx->dTb.reserve(tbStride * static_cast<size_t>(std::max(gridA, gridB))));
+    if (needWide) TWL_CUDA(ctx, ctx->dState.reserve(stateStride * static_cast<size_t>(gridB)));
+
+    const int counters[4] = {0, n, 0, 0};
+    TWL_CUDA(ctx, cudaMemcpyAsync(ctx->dCounters.ptr, counters, sizeof(counters), cudaMemcpyHostToDevice, ctx->stream));
+    TWL_CUDA(ctx, cudaEventRecord(ctx->evStart, ctx->stream));
+
+    twl::TalcoArgs a{};
+    a.prof = ctx->dProf.ptr;
+    a.pairs = ctx->dPairs.ptr;
+    a.results = ctx->dResults.ptr;
+    a.paths = ctx->dPaths.ptr;
+    a.marker = ctx->marker;
+    a.gapOpen = ctx->gapOpen;
+    a.gapExtend = ctx->gapExtend;
+    a.score = ctx->dScore.ptr;
+    a.tbScratch = ctx->dTb.ptr;
+    a.tbStride = tbStride;
+
+    // narrow variant: wavefront state in shared memory; pairs that outgrow it are appended to dOverflow
+    a.order = ctx->dOrder.ptr;
+    a.queue = ctx->dCounters.ptr + 0;
+    a.nWorkPtr = ctx->dCounters.ptr + 1;
+    a.overflowList = needWide ? ctx->dOverflow.ptr : nullptr;
+    a.overflowCount = ctx->dCounters.ptr + 3;
+    a.stateScratch = nullptr;
+    a.stateStride = 0;
+    a.stateCap = std::min(kSmemStateCap, wideCap);
+    TWL_CUDA(ctx, twl::launchTalcoGeneric(ctx->P, false, a, gridA, twl::genericStateWords(a.stateCap) * sizeof(float), ctx->stream));
+    ctx->lastLaunches += 1;
+    if (needWide) {
+        // wide variant over the overflow list (count read on the device, no host round trip)
+        a.order = ctx->dOverflow.ptr;
+        a.queue = ctx->dCounters.ptr + 2;
+        a.nWorkPtr = ctx->dCounters.ptr + 3;
+        a.overflowList = nullptr;
+        a.overflowCount = nullptr;
+        a.stateScratch = ctx->dState.ptr;
+        a.stateStride = stateStride;
+        a.stateCap = wideCap;
+        TWL_CUDA(ctx, twl::launchTalcoGeneric(ctx->P, true, a, gridB, 0, ctx->stream));
+        ctx->lastLaunches += 1;
+    }
+    TWL_CUDA(ctx, cudaEventRecord(ctx->evStop, ctx->stream));
+    ctx->timingPending = true;
+    ctx->ran = true;
+    return TWL_OK;
+}
+
+int twl_batch_fetch(twl_ctx *ctx, int8_t *const *paths, twl_pair_result *results) {
+    if (!ctx) return TWL_E_ARG;
+    if (!ctx->ran) return fail(ctx, TWL_E_STATE, "twl_batch_fetch: no batch has been run");
+    cudaSetDevice(ctx->device);
+    const int n = ctx->nPairs;
+    if (n == 0) return TWL_OK;
+    TWL_CUDA(ctx, ctx->hResults.reserve(n));
+    TWL_CUDA(ctx, cudaMemcpyAsync(ctx->hResults.ptr, ctx->dResults.ptr, n * sizeof(twl::DevResult), cudaMemcpyDeviceToHost, ctx->stream));
+    if (paths) {
+        TWL_CUDA(ctx, ctx->hPaths.reserve(ctx->pathBytes));
+        TWL_CUDA(ctx, cudaMemcpyAsync(ctx->hPaths.ptr, ctx->dPaths.ptr, ctx->pathBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int p = 0; p < n; ++p) {
+        const twl::DevResult &r = ctx->hResults.ptr[p];
+        if (results) {
+            results[p].status = r.status;
+            results[p].path_len = r.pathLen;
+            results[p].tiles = r.tiles;
+            results[p].reserved = 0;
+            results[p].cells = r.cells;
+            results[p].diagonals = r.diagonals;
+        }
+        if (paths && paths[p] && r.status == 0 && r.pathLen > 0)
+            std::memcpy(paths[p], ctx->hPaths.ptr + ctx->hPairs[p].alnOff, static_cast<size_t>(r.pathLen));
+    }
+    return TWL_OK;
+}
+
+int twl_align_profiles(twl_ctx *ctx, const twl_profile_pair *pairs, int n_pairs, int8_t *const *paths, twl_pair_result *results) {
+    int rc = twl_batch_stage(ctx, pairs, n_pairs);
+    if (rc != TWL_OK) return rc;
+    rc = twl_batch_run(ctx);
+    if (rc != TWL_OK) return rc;
+    return twl_batch_fetch(ctx, paths, results);
+}
+
+float twl_last_kernel_ms(const twl_ctx *ctx) {
+    if (!ctx) return -1.0f;
+    twl_ctx *c = const_cast<twl_ctx *>(ctx);
+    if (c->timingPending) {
+        cudaSetDevice(c->device);
+        float ms = 0.0f;
+        if (cudaEventSynchronize(c->evStop) == cudaSuccess && cudaEventElapsedTime(&ms, c->evStart, c->evStop) == cudaSuccess) c->lastMs = ms;
+        c->timingPending = false;
+    }
+    return c->lastMs;
+}
+
+int twl_last_launch_count(const twl_ctx *ctx) { return ctx ? ctx->lastLaunches : 0; }
+
+} // extern "C"
