@@ -1,0 +1,266 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the per-level TALCO-XDrop alignment path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs P] [--length L] [--impl reference]
+
+A "step" is one pass of the hot path over one level-shaped batch of synthetic profile pairs (RNASim-shaped: ~1.5 kb
+profiles of 1-8 sequences per side; BASELINE.json configs[1] shape, synthetic because the bundled files are not on the
+GPU box and a single 579-sequence tree cannot fill a B200). Metric = DP giga cell-updates per second (GCUPS), cells
+counted by the kernel with the reference's definition (sum over anti-diagonals of the live band width).
+
+  value  : kernels only, batch resident in HBM, CUDA events on the launching stream (max over ranks)
+  e2e    : the same batch through twl_align_profiles() with HOST buffers: pack + H2D + kernels + D2H, host wall clock
+  roofline: the DP kernel against the FP32 pipe peak (117 FP32 op per nucleotide cell-update)
+  cpu_baseline: the reference's own Talco_xdrop::Align_freq (oracle/_ref/libtalco_ref.so when present, else the
+           oracle port) on a bounded sample of the same batch, all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_CELL_NT = 117.0
+N_SM, LANES = 148, 128
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    sm_mhz, hbm, src = 1965.0, 6650.0, "fallback"
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        sm_mhz, hbm, src = float(p.get("sm_max_mhz", sm_mhz)), float(p.get("hbm_gbs", hbm)), "measured"
+    fp32_tflops = N_SM * LANES * 2 * sm_mhz * 1e6 / 1e12
+    return dict(fp32_tflops=fp32_tflops, hbm_gbs=hbm, source=src, sm_mhz=sm_mhz)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_batch(n_pairs, length, seed):
+    from twilight_b200 import ProfilePairIn, synth
+    raw = synth.profile_pair_batch(n_pairs, length, seed=seed, kind="rna")
+    return raw, [ProfilePairIn(**p) for p in raw]
+
+
+def cpu_reference_gcups(raw_pairs, sample_pairs, threads):
+    """Times the reference's Align_freq (or the port) on `sample_pairs` pairs with `threads` host threads."""
+    from concurrent.futures import ThreadPoolExecutor
+    from tests import oracle_lib as ol
+    cfg = ol.TalcoCfg()
+    use_ref = ol.have_ref()
+    sample = raw_pairs[:sample_pairs]
+
+    def one(p):
+        args = (cfg, p["freq_ref"], p["freq_qry"], p["gap_open_ref"], p["gap_ext_ref"], p["gap_open_qry"], p["gap_ext_qry"],
+                p["ref_num"], p["qry_num"])
+        if use_ref:
+            ol.ref_talco(*args)
+        return 0
+    # cell counts come from the port (same definition as the kernel's counter); not part of the timed region
+    cells = sum(ol.port_talco(cfg, p["freq_ref"], p["freq_qry"], p["gap_open_ref"], p["gap_ext_ref"], p["gap_open_qry"],
+                              p["gap_ext_qry"], p["ref_num"], p["qry_num"])[2] for p in sample)
+    if not use_ref:
+        def one(p):  # noqa: F811
+            ol.port_talco(cfg, p["freq_ref"], p["freq_qry"], p["gap_open_ref"], p["gap_ext_ref"], p["gap_open_qry"],
+                          p["gap_ext_qry"], p["ref_num"], p["qry_num"])
+            return 0
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(one, sample))
+    dt = time.perf_counter() - t0
+    return cells / dt / 1e9, cells, dt, ("reference" if use_ref else "port")
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_sample = max(threads, min(args.pairs, 4 * threads))
+    raw, _ = make_batch(n_sample, args.length, seed=1234)
+    vals, ms = [], []
+    kind = "port"
+    for s in range(args.warmup + args.steps):
+        g, cells, dt, kind = cpu_reference_gcups(raw, n_sample, threads)
+        if s >= args.warmup:
+            vals.append(g)
+            ms.append(dt * 1e3)
+    v = float(np.mean(vals))
+    line = {"impl": "reference", "metric": "dp_gcups", "value": v, "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"level batch of RNASim-shaped profile pairs (~{args.length} columns, 1-8 sequences per side)",
+                       "pairs_per_step": n_sample, "l2": "inputs are host-resident (CPU run)"},
+            "cpu_baseline": {"value": v, "unit": "GCUPS", "cores": threads, "kind": kind,
+                             "sample": f"{n_sample} pairs of the same generator per step, Talco_xdrop::Align_freq only"},
+            "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--pairs", type=int, default=4096, help="profile pairs per GPU per step")
+    ap.add_argument("--length", type=int, default=1500)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import twilight_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(local)
+
+    # weak scaling: every rank aligns its own shard of same-level pairs (no data-path collective)
+    raw, pairs = make_batch(args.pairs, args.length, seed=1000 + rank)
+    ctx = twilight_b200.Context(device=local)
+    ctx.stage(pairs)
+    in_bytes = sum(p.freq_ref.nbytes + p.freq_qry.nbytes + 2 * (p.gap_open_ref.nbytes + p.gap_open_qry.nbytes) for p in pairs)
+    # L2 hygiene: the staged batch is read once per step and exceeds L2 (126 MB) at the default size; a flush buffer is
+    # written between timed steps anyway
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        ctx.run()
+        ctx.kernel_ms()
+    outs = ctx.fetch(want_paths=False)
+    cells = sum(o.cells for o in outs)
+    bad = sum(1 for o in outs if o.status != 0)
+
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    step_ms, launches = [], 0
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        ctx.run()
+        step_ms.append(ctx.kernel_ms())
+        launches += ctx.launch_count()
+    barrier()
+    clocks = sampler.stop()
+    dev_ms = float(np.sum(step_ms))
+
+    # e2e: host buffers in, host buffers out, every step
+    e2e_ms = []
+    for s in range(1 + args.steps):
+        t0 = time.perf_counter()
+        outs2 = ctx.align_profiles(pairs)
+        if s > 0:
+            e2e_ms.append((time.perf_counter() - t0) * 1e3)
+    d2h = sum(len(o.path) for o in outs2) + 40 * len(outs2)
+    e2e_total_ms = float(np.sum(e2e_ms))
+
+    tot = torch.tensor([dev_ms, e2e_total_ms, float(cells)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        mx = tot.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tot.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_total_ms, cells_all = float(mx[0]), float(mx[1]), float(sm[2])
+    else:
+        cells_all = float(cells)
+
+    if rank == 0:
+        pk = peaks()
+        gcups = cells_all * args.steps / (dev_ms * 1e-3) / 1e9
+        e2e_gcups = cells_all * args.steps / (e2e_total_ms * 1e-3) / 1e9
+        per_gpu_gcups = cells * args.steps / (float(np.sum(step_ms)) * 1e-3) / 1e9
+        achieved_tflops = per_gpu_gcups * 1e9 * FLOP_PER_CELL_NT / 1e12
+        line = {"metric": "dp_gcups", "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"level batch of RNASim-shaped profile pairs (~{args.length} columns, 1-8 sequences per side), "
+                                       "TALCO-XDrop DP + traceback", "pairs_per_gpu": args.pairs, "cells_per_step": cells_all,
+                           "failed_pairs": bad, "l2": "256 MiB flush buffer written between timed steps"},
+                "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(d2h),
+                        "ms_per_step": e2e_total_ms / args.steps},
+                "gpu_launches": launches,
+                "roofline": {"bound": "fp32-pipe", "achieved": achieved_tflops, "peak": pk["fp32_tflops"], "unit": "TFLOP/s",
+                             "frac": achieved_tflops / pk["fp32_tflops"], "traffic": None,
+                             "note": f"DP kernel is CUDA-core bound (SURVEY.md §8d): 117 FP32 op/cell x GCUPS; peak = 148 SM x 128 lanes x 2 x "
+                                     f"{pk['sm_mhz']:.0f} MHz ({pk['source']} sm_max_mhz); per GPU"},
+                "seqs_per_s": None,
+                "clocks": clocks}
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            n_sample = max(threads, min(len(raw), 4 * threads))
+            g, c, dt, kind = cpu_reference_gcups(raw, n_sample, threads)
+            line["cpu_baseline"] = {"value": g, "unit": "GCUPS", "cores": threads, "kind": kind,
+                                    "sample": f"{n_sample} pairs of the step's batch ({c} cells, {dt:.1f} s), Talco_xdrop::Align_freq only"}
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

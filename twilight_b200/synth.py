@@ -158,3 +158,68 @@ def levels_bottom_up(tree: Tree):
             lvl[v] = 1 + max(lvl[c] for c in ch)
             out.setdefault(int(lvl[v]) - 1, []).append((ch[0], ch[1], v))
     return [out[k] for k in sorted(out)]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Level-shaped batches of profile pairs (inputs at the Align_freq boundary) without running an aligner: each side is a
+# small star-shaped family whose members differ from the family ancestor by substitutions and masked-out deletions, so
+# the family is trivially aligned; the two family ancestors are diverged with indels like siblings of a guide tree.
+# ------------------------------------------------------------------------------------------------------------------
+def _letters_to_index(seq: np.ndarray, kind: str) -> np.ndarray:
+    lut = np.full(256, 4 if kind != "protein" else 20, np.int64)
+    if kind == "protein":
+        for n, ch in enumerate(AA):
+            lut[ch] = n
+        lut[ord("-")] = 21
+    else:
+        for ch, n in ((ord("A"), 0), (ord("C"), 1), (ord("G"), 2), (ord("T"), 3), (ord("U"), 3)):
+            lut[ch] = n
+        lut[ord("-")] = 5
+    return lut[seq]
+
+
+def family_profile(anc: np.ndarray, members: int, rng, kind: str, sub_rate=0.08, del_rate=0.02, gap_open=-50.0,
+                   gap_extend=-5.0):
+    """Weighted column counts [len][P] (columns sum to `members`), and position-specific gap penalties computed with the
+    ClustalW-style rule of calculatePSGP (alignment-helper.cpp:168-219)."""
+    alphabet = {"rna": RNA, "dna": NT, "protein": AA}[kind]
+    P = 22 if kind == "protein" else 6
+    L = len(anc)
+    w = rng.uniform(0.5, 1.5, members).astype(np.float32)
+    w = (w / w.sum() * members).astype(np.float32)
+    prof = np.zeros((L, P), np.float32)
+    for m in range(members):
+        s = anc.copy()
+        hit = rng.random(L) < sub_rate
+        s[hit] = rng.choice(alphabet, size=int(hit.sum()))
+        if members > 1 and del_rate > 0:
+            starts = np.flatnonzero(rng.random(L) < del_rate / 3)
+            for st in starts:
+                s[st:st + int(rng.geometric(0.4))] = ord("-")
+        idx = _letters_to_index(s, kind)
+        np.add.at(prof, (np.arange(L), idx), w[m])
+    g = prof[:, P - 1].astype(np.float64)
+    scale = 1.0 if kind == "protein" else 0.5
+    keep = (members - g) / members
+    gop = np.where(g > 0, np.minimum(np.float32(gap_open * 0.1), (np.float32(gap_open * scale) * keep).astype(np.float32)), np.float32(gap_open))
+    gex = np.where(g > 0, np.minimum(np.float32(gap_extend * 0.2), (gap_extend * keep).astype(np.float32)), np.float32(gap_extend))
+    return prof, gop.astype(np.float32), gex.astype(np.float32), float(members)
+
+
+def profile_pair_batch(n_pairs: int, length: int, seed: int = 0, kind: str = "rna", members=(1, 2, 4, 8),
+                       divergence: float = 0.15, indel_rate: float = 0.03):
+    """n_pairs sibling profile pairs of ~`length` columns. Returns a list of dicts with the twl_profile_pair fields."""
+    rng = np.random.default_rng(seed)
+    alphabet = {"rna": RNA, "dna": NT, "protein": AA}[kind]
+    probs = AA_FREQ / AA_FREQ.sum() if kind == "protein" else None
+    out = []
+    for _ in range(n_pairs):
+        root = rng.choice(alphabet, size=int(length * rng.uniform(0.97, 1.03)), p=probs)
+        a = _mutate(root, divergence / 2, rng, alphabet, indel_rate, probs)
+        b = _mutate(root, divergence / 2, rng, alphabet, indel_rate, probs)
+        ma, mb = int(rng.choice(members)), int(rng.choice(members))
+        fr, gor, ger, nr = family_profile(a, ma, rng, kind)
+        fq, goq, geq, nq = family_profile(b, mb, rng, kind)
+        out.append(dict(freq_ref=fr, freq_qry=fq, gap_open_ref=gor, gap_ext_ref=ger, gap_open_qry=goq, gap_ext_qry=geq,
+                        ref_num=nr, qry_num=nq))
+    return out
