@@ -98,6 +98,10 @@ int twl_batch_fetch(twl_ctx *ctx, int8_t *const *paths, twl_pair_result *results
 float twl_last_kernel_ms(const twl_ctx *ctx);
 int twl_last_launch_count(const twl_ctx *ctx);
 
+/* Tuning / diagnostics switches. "force_generic" = 1 routes nucleotide batches through the wide-band generic kernel
+ * instead of the register-resident wavefront kernel (results are identical; used by the A/B parity tests). */
+int twl_set_option(twl_ctx *ctx, const char *name, int value);
+
 /* Library build information (arch string etc.). */
 const char *twl_version(void);
 

@@ -109,3 +109,34 @@ def test_empty_batch_and_tiny_pairs(ctxs):
     for o, w in zip(outs, wants):
         assert o.status == w[1]
         assert np.array_equal(o.path, w[0])
+
+
+@pytest.mark.parametrize("n,L,seed,marker", [(12, 700, 2, 128), (16, 1500, 1, 1024)])
+def test_generic_kernel_matches_port(n, L, seed, marker):
+    """The wide-band generic kernel (the fallback of the register-resident wavefront kernel) stays parity-green."""
+    import twilight_b200
+    cfg, _, _, _, recs = synthetic_records(n, L, seed, marker)
+    ctx = twilight_b200.Context(marker=marker)
+    ctx.set_option("force_generic", 1)
+    outs = ctx.align_profiles(records_to_pairs(recs, cfg))
+    ctx.close()
+    for k, (o, r) in enumerate(zip(outs, recs)):
+        assert o.status == r.error == 0
+        assert o.cells == r.cells and o.tiles == r.tiles
+        assert np.array_equal(o.path, r.aln_wo), f"pair {k}"
+
+
+def test_band_overflow_chain(ctxs):
+    """x-drop values that push the band over 512 and over 1024 cells walk the kernel chain wavefront<128> ->
+    wavefront<256> -> generic and must still equal the oracle."""
+    import twilight_b200
+    cfg, _, _, _, recs = synthetic_records(2, 2400, 19, 1024)
+    r = recs[0]
+    for xdrop in (9000, 14000, 40000):
+        c = ol.TalcoCfg(xdrop=xdrop)
+        want, err, cells, tiles, _ = ol.port_talco(c, r.profile[0], r.profile[1], r.gap_op[0], r.gap_ex[0], r.gap_op[1], r.gap_ex[1], 1, 1)
+        pair = twilight_b200.ProfilePairIn(r.profile[0], r.profile[1], r.gap_op[0], r.gap_ex[0], r.gap_op[1], r.gap_ex[1], 1, 1, xdrop=xdrop)
+        out = ctxs(1024).align_profiles([pair])[0]
+        assert out.status == err == 0, xdrop
+        assert out.cells == cells, xdrop
+        assert np.array_equal(out.path, want), xdrop

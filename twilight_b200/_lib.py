@@ -38,6 +38,7 @@ SIGNATURES = {
     "twl_batch_fetch": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(PairResult)]),
     "twl_last_kernel_ms": (C.c_float, [C.c_void_p]),
     "twl_last_launch_count": (C.c_int, [C.c_void_p]),
+    "twl_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "twl_version": (C.c_char_p, []),
 }
 

@@ -82,6 +82,9 @@ class Context:
         if rc != 0:
             raise TwilightError(f"{_lib.ERRORS.get(rc, rc)}: {self._lib.twl_last_error(self._h).decode()}")
 
+    def set_option(self, name: str, value: int):
+        self._check(self._lib.twl_set_option(self._h, name.encode(), int(value)))
+
     def close(self):
         if self._h:
             self._lib.twl_destroy(self._h)

@@ -16,6 +16,9 @@ namespace twl {
 size_t genericStateWords(int stateCap);
 cudaError_t launchTalcoGeneric(int P, bool globalState, const TalcoArgs &args, int grid, size_t dynSmemBytes, cudaStream_t stream);
 int genericThreads();
+int wavefrontBandCapacity(int threads);
+cudaError_t launchTalcoWavefront(int threads, const TalcoArgs &args, int grid, cudaStream_t stream);
+int wavefrontMaxCtasPerSm(int threads);
 } // namespace twl
 
 namespace {
@@ -72,6 +75,7 @@ struct twl_ctx {
     float gapOpen = 0, gapExtend = 0, gapBoundary = 0;
     int marker = twl::kMaxMarker;
     DevBuf<float> dScore;
+    std::vector<float> hScore;
 
     // staged batch
     int nPairs = 0;
@@ -92,6 +96,7 @@ struct twl_ctx {
     DevBuf<uint8_t> dTb;
     DevBuf<float> dState;
 
+    bool forceGeneric = false;   // route nucleotide batches through the generic kernel (A/B parity + benchmarking)
     float lastMs = -1.0f;
     int lastLaunches = 0;
     bool timingPending = false;
@@ -191,6 +196,7 @@ int twl_set_params(twl_ctx *ctx, const float *score, int M, float gap_open, floa
     TWL_CUDA(ctx, ctx->dScore.reserve(static_cast<size_t>(M) * M));
     TWL_CUDA(ctx, cudaMemcpyAsync(ctx->dScore.ptr, score, sizeof(float) * M * M, cudaMemcpyHostToDevice, ctx->stream));
     TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->hScore.assign(score, score + static_cast<size_t>(M) * M);
     ctx->M = M;
     ctx->P = M + 1;
     ctx->gapOpen = gap_open;
@@ -291,16 +297,44 @@ int twl_batch_run(twl_ctx *ctx) {
     ctx->timingPending = false;
     if (ctx->nPairs == 0) { ctx->ran = true; return TWL_OK; }
     const int n = ctx->nPairs;
-    const int gridA = std::min(n, ctx->smCount * kNarrowCtasPerSm);
-    const int gridB = std::min(n, ctx->smCount);
-    const int wideCap = std::max(ctx->maxFLen, 8);
-    const bool needWide = wideCap > kSmemStateCap;
-    const size_t tbStride = tbBytesPerCta(ctx->marker);
-    const size_t stateStride = twl::genericStateWords(wideCap);
-    TWL_CUDA(ctx, ctx->dTb.reserve(tbStride * static_cast<size_t>(std::max(gridA, gridB))));
-    if (needWide) TWL_CUDA(ctx, ctx->dState.reserve(stateStride * static_cast<size_t>(gridB)));
+    const int marker = ctx->marker;
+    const int wideCap = std::max(ctx->maxFLen, 8);                 // widest band any pair of the batch may legally reach
+    const bool nucleotide = (ctx->P == 6) && !ctx->forceGeneric;
 
-    const int counters[4] = {0, n, 0, 0};
+    // Kernel chain. Every stage reads its work list + count from device memory and appends the pairs whose band
+    // outgrew its capacity to the next stage's list, so the whole chain is enqueued without a host round trip.
+    //   nucleotide: wavefront<128> (band <= 512) -> wavefront<256> (band <= 1024) -> generic/global state (any band)
+    //   protein   : generic/shared state (band <= 1020)                            -> generic/global state
+    struct Stage { int kind; int threads; int cap; int grid; size_t tbStride; };   // kind 0 wavefront, 1 generic smem, 2 generic global
+    std::vector<Stage> stages;
+    auto tbRows = [&](int w) { return (static_cast<size_t>(marker + 1) * w + 255) & ~static_cast<size_t>(255); };
+    if (nucleotide) {
+        for (int threads : {128, 256}) {
+            const int cap = twl::wavefrontBandCapacity(threads);
+            const int perSm = std::max(1, twl::wavefrontMaxCtasPerSm(threads));
+            stages.push_back({0, threads, cap, std::min(n, ctx->smCount * perSm), tbRows(cap)});
+            if (wideCap <= cap) break;
+        }
+    } else {
+        const int cap = std::min(kSmemStateCap, wideCap);
+        stages.push_back({1, twl::genericThreads(), cap, std::min(n, ctx->smCount * kNarrowCtasPerSm), tbBytesPerCta(marker)});
+    }
+    if (wideCap > stages.back().cap) stages.push_back({2, twl::genericThreads(), wideCap, std::min(n, ctx->smCount), tbBytesPerCta(marker)});
+
+    size_t tbBytes = 0, stateWords = 0;
+    for (const Stage &st : stages) {
+        tbBytes = std::max(tbBytes, st.tbStride * static_cast<size_t>(st.grid));
+        if (st.kind == 2) stateWords = twl::genericStateWords(st.cap) * static_cast<size_t>(st.grid);
+    }
+    TWL_CUDA(ctx, ctx->dTb.reserve(tbBytes));
+    if (stateWords) TWL_CUDA(ctx, ctx->dState.reserve(stateWords));
+    const int nStages = static_cast<int>(stages.size());
+    TWL_CUDA(ctx, ctx->dOverflow.reserve(static_cast<size_t>(n) * std::max(1, nStages - 1)));
+
+    // counters: [2*s] = queue cursor of stage s, [2*s+1] = work count of stage s
+    int counters[16] = {0};
+    counters[1] = n;
+    TWL_CUDA(ctx, ctx->dCounters.reserve(16));
     TWL_CUDA(ctx, cudaMemcpyAsync(ctx->dCounters.ptr, counters, sizeof(counters), cudaMemcpyHostToDevice, ctx->stream));
     TWL_CUDA(ctx, cudaEventRecord(ctx->evStart, ctx->stream));
 
@@ -309,35 +343,26 @@ int twl_batch_run(twl_ctx *ctx) {
     a.pairs = ctx->dPairs.ptr;
     a.results = ctx->dResults.ptr;
     a.paths = ctx->dPaths.ptr;
-    a.marker = ctx->marker;
+    a.marker = marker;
     a.gapOpen = ctx->gapOpen;
     a.gapExtend = ctx->gapExtend;
     a.score = ctx->dScore.ptr;
+    if (ctx->P == 6) std::memcpy(a.scoreNt, ctx->hScore.data(), sizeof(a.scoreNt));
     a.tbScratch = ctx->dTb.ptr;
-    a.tbStride = tbStride;
-
-    // narrow variant: wavefront state in shared memory; pairs that outgrow it are appended to dOverflow
-    a.order = ctx->dOrder.ptr;
-    a.queue = ctx->dCounters.ptr + 0;
-    a.nWorkPtr = ctx->dCounters.ptr + 1;
-    a.overflowList = needWide ? ctx->dOverflow.ptr : nullptr;
-    a.overflowCount = ctx->dCounters.ptr + 3;
-    a.stateScratch = nullptr;
-    a.stateStride = 0;
-    a.stateCap = std::min(kSmemStateCap, wideCap);
-    TWL_CUDA(ctx, twl::launchTalcoGeneric(ctx->P, false, a, gridA, twl::genericStateWords(a.stateCap) * sizeof(float), ctx->stream));
-    ctx->lastLaunches += 1;
-    if (needWide) {
-        // wide variant over the overflow list (count read on the device, no host round trip)
-        a.order = ctx->dOverflow.ptr;
-        a.queue = ctx->dCounters.ptr + 2;
-        a.nWorkPtr = ctx->dCounters.ptr + 3;
-        a.overflowList = nullptr;
-        a.overflowCount = nullptr;
-        a.stateScratch = ctx->dState.ptr;
-        a.stateStride = stateStride;
-        a.stateCap = wideCap;
-        TWL_CUDA(ctx, twl::launchTalcoGeneric(ctx->P, true, a, gridB, 0, ctx->stream));
+    for (int s = 0; s < nStages; ++s) {
+        const Stage &st = stages[s];
+        const bool hasNext = (s + 1 < nStages);
+        a.order = (s == 0) ? ctx->dOrder.ptr : ctx->dOverflow.ptr + static_cast<size_t>(n) * (s - 1);
+        a.queue = ctx->dCounters.ptr + 2 * s;
+        a.nWorkPtr = ctx->dCounters.ptr + 2 * s + 1;
+        a.overflowList = hasNext ? ctx->dOverflow.ptr + static_cast<size_t>(n) * s : nullptr;
+        a.overflowCount = hasNext ? ctx->dCounters.ptr + 2 * (s + 1) + 1 : nullptr;
+        a.tbStride = st.tbStride;
+        a.stateCap = st.cap;
+        a.stateScratch = (st.kind == 2) ? ctx->dState.ptr : nullptr;
+        a.stateStride = (st.kind == 2) ? twl::genericStateWords(st.cap) : 0;
+        if (st.kind == 0) TWL_CUDA(ctx, twl::launchTalcoWavefront(st.threads, a, st.grid, ctx->stream));
+        else TWL_CUDA(ctx, twl::launchTalcoGeneric(ctx->P, st.kind == 2, a, st.grid, st.kind == 1 ? twl::genericStateWords(st.cap) * sizeof(float) : 0, ctx->stream));
         ctx->lastLaunches += 1;
     }
     TWL_CUDA(ctx, cudaEventRecord(ctx->evStop, ctx->stream));
@@ -381,6 +406,12 @@ int twl_align_profiles(twl_ctx *ctx, const twl_profile_pair *pairs, int n_pairs,
     rc = twl_batch_run(ctx);
     if (rc != TWL_OK) return rc;
     return twl_batch_fetch(ctx, paths, results);
+}
+
+int twl_set_option(twl_ctx *ctx, const char *name, int value) {
+    if (!ctx || !name) return TWL_E_ARG;
+    if (std::strcmp(name, "force_generic") == 0) { ctx->forceGeneric = value != 0; return TWL_OK; }
+    return fail(ctx, TWL_E_ARG, std::string("twl_set_option: unknown option ") + name);
 }
 
 float twl_last_kernel_ms(const twl_ctx *ctx) {

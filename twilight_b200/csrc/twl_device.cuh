@@ -52,7 +52,8 @@ struct TalcoArgs {
     int *overflowCount;
     int marker;
     float gapOpen, gapExtend;
-    const float *score;      // (P-1)^2 row-major
+    const float *score;      // (P-1)^2 row-major (device)
+    float scoreNt[25];       // the same matrix by value for the nucleotide kernels (lands in the constant bank)
     uint8_t *tbScratch;      // per-CTA traceback bytes
     size_t tbStride;
     float *stateScratch;     // per-CTA wavefront state when it does not fit in shared memory
