@@ -102,6 +102,10 @@ int twl_last_launch_count(const twl_ctx *ctx);
  * instead of the register-resident wavefront kernel (results are identical; used by the A/B parity tests). */
 int twl_set_option(twl_ctx *ctx, const char *name, int value);
 
+/* Device self-test: evaluates the reciprocal-based exact division used by the DP kernels and the IEEE divide on n
+ * operand pairs and reports on how many they differ bit-wise (must be 0). */
+int twl_selftest_division(twl_ctx *ctx, const float *num, const float *den, int n, int *mismatches);
+
 /* Library build information (arch string etc.). */
 const char *twl_version(void);
 

@@ -140,3 +140,36 @@ def test_band_overflow_chain(ctxs):
         assert out.status == err == 0, xdrop
         assert out.cells == cells, xdrop
         assert np.array_equal(out.path, want), xdrop
+
+
+def test_exact_division_selftest(ctxs):
+    """The reciprocal-based division inside the DP kernels must be bit-identical to the IEEE divide."""
+    rng = np.random.default_rng(0)
+    n = 4_000_000
+    den = rng.integers(1, 20000, n).astype(np.float32) * rng.integers(1, 20000, n).astype(np.float32)
+    den[: n // 4] = rng.integers(1, 5000, n // 4).astype(np.float32)
+    num = (rng.standard_normal(n) * np.exp(rng.uniform(-12, 25, n))).astype(np.float32)
+    num[::97] = 0.0
+    num[1::97] = rng.integers(-4000, 4000, len(num[1::97])).astype(np.float32) * 18
+    assert ctxs(1024).selftest_division(num, den) == 0
+
+
+@pytest.mark.parametrize("which", ["wildcard", "random"])
+def test_unstructured_matrix_path(which):
+    """Matrices without the built-in nucleotide shape (e.g. --wildcard, --matrix) take the generic 5x5 score path of the
+    wavefront kernel."""
+    import twilight_b200
+    if which == "wildcard":
+        score = ol.nt_matrix(wildcard=True)
+    else:
+        score = np.random.default_rng(4).integers(-9, 12, (5, 5)).astype(np.float32)
+        score = ((score + score.T) / 2).astype(np.float32)
+    cfg = ol.TalcoCfg(score=score, marker=256)
+    _, _, _, _, recs = synthetic_records(10, 900, 21, 256, cfg=cfg)
+    ctx = twilight_b200.Context(score=score, marker=256)
+    outs = ctx.align_profiles(records_to_pairs(recs, cfg))
+    ctx.close()
+    for k, (o, r) in enumerate(zip(outs, recs)):
+        assert o.status == r.error == 0
+        assert o.cells == r.cells
+        assert np.array_equal(o.path, r.aln_wo), f"pair {k}"

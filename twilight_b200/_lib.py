@@ -39,6 +39,7 @@ SIGNATURES = {
     "twl_last_kernel_ms": (C.c_float, [C.c_void_p]),
     "twl_last_launch_count": (C.c_int, [C.c_void_p]),
     "twl_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "twl_selftest_division": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "twl_version": (C.c_char_p, []),
 }
 

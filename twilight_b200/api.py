@@ -85,6 +85,13 @@ class Context:
     def set_option(self, name: str, value: int):
         self._check(self._lib.twl_set_option(self._h, name.encode(), int(value)))
 
+    def selftest_division(self, num: np.ndarray, den: np.ndarray) -> int:
+        num = np.ascontiguousarray(num, np.float32)
+        den = np.ascontiguousarray(den, np.float32)
+        bad = C.c_int(0)
+        self._check(self._lib.twl_selftest_division(self._h, num.ctypes.data, den.ctypes.data, int(num.size), C.byref(bad)))
+        return bad.value
+
     def close(self):
         if self._h:
             self._lib.twl_destroy(self._h)

@@ -8,6 +8,19 @@
 
 namespace twl {
 
+// num/den rounded to nearest, bit-identical to IEEE division (Markstein: with rcp = RN(1/den), q = RN(num*rcp),
+// r = num - den*q exactly by FMA, RN(q + r*rcp) is the correctly rounded quotient). Tiny numerators (where q could be
+// subnormal) take the IEEE divide.
+__device__ __forceinline__ float exactDiv(float num, float den, float rcp) {
+    const float q = __fmul_rn(num, rcp);
+    const float r = __fmaf_rn(-q, den, num);
+    float res = __fmaf_rn(r, rcp, q);
+    const float an = fabsf(num);
+    if (an < 1e-18f && an > 0.0f) res = __fdiv_rn(num, den);
+    return res;
+}
+
+
 // Nucleotide, P = 6. r[0..5], q[0..5] are profile columns, S the 5x5 matrix (row-major, any address space), g the
 // gap-character score.
 template <typename MatPtr>

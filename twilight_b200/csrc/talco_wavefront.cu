@@ -2,22 +2,25 @@
 // wavefront lives in REGISTERS.
 //
 // Mapping. A CTA of NT threads owns W = 4*NT consecutive query rows at a time. Row i is handled by "slot"
-// rho = i mod W, i.e. thread rho/4, register slot rho%4; as the live band [L,U] of the X-drop recurrence slides
-// along the query, a slot whose row fell below L is re-assigned to row + W. Per slot the thread keeps, in registers,
-// the query column (6 counts + 2 position-specific gap penalties) and the H / I / D scores of the previous two
-// anti-diagonals, so per cell and per diagonal the only memory traffic is one 32-byte reference column (two LDG.128
-// that hit L1; the columns needed a few diagonals ahead are prefetched) and one traceback byte (the four slots of a
-// thread store one coalesced 32-bit word). Row-neighbour values come from the thread's own registers for slots 1..3
-// and from one warp shuffle for slot 0; warps exchange their edge values and the per-diagonal reduction
-// (running maximum for the X-drop rule, first / last live row) through shared memory with ONE barrier per diagonal.
+// rho = i mod W, i.e. thread rho/4, register slot rho%4 (a thread owns 4 consecutive rows); as the live band [L,U] of
+// the X-drop recurrence slides along the query, a thread whose rows fell below L is re-assigned to rows + W. Per
+// slot the thread keeps, in registers, the query column (6 counts + 2 position-specific gap penalties) and the
+// H / I / D scores of the previous two anti-diagonals, so per cell and per diagonal the only memory traffic is one
+// 32-byte reference column (two LDG.128 that hit L1; the lines needed a few diagonals ahead are prefetched) and one
+// traceback byte (the four slots of a thread store one coalesced 32-bit word). Row-neighbour values come from the
+// thread's own registers for slots 1..3 and from one warp shuffle for slot 0; warps exchange their edge values and the
+// per-diagonal reduction (running maximum for the X-drop rule, first / last live row) through shared memory with ONE
+// barrier per diagonal. The four cells of a thread are evaluated branch-free so that their dependent FP chains
+// interleave; warps that hold no live cell skip the evaluation.
 //
 // What is kept bit-identical to the reference CPU path (src/TALCO-XDrop.cpp:233-689): the float operation order of
-// the score (talco_score.cuh), tie rules, the prune rule against the previous diagonal's maximum, the dead-end
-// trimming, the convergence pointers INCLUDING the reference's rotating buffers indexed by (row - L[k]) — those
-// live in shared memory with the reference's indexing so that the stale slots the reference reads are reproduced —
-// the tile stop rule, the traceback start cell and the per-tile path concatenation of Align_freq (:62-108).
+// the score (see talco_score.cuh; the "DNA3Z" fast path below only drops terms that are exact zeros), tie rules, the
+// prune rule against the previous diagonal's maximum, dead-end trimming, the convergence pointers INCLUDING the
+// reference's rotating buffers indexed by (row - L[k]) — those live in shared memory with the reference's indexing so
+// that the stale slots the reference reads are reproduced — the tile stop rule, the traceback start cell and the
+// per-tile path concatenation of Align_freq (:62-108).
 //
-// A band wider than W cannot be held; the pair is then appended to an overflow list and re-run by a wider
+// A band wider than W-3 cannot be held; the pair is then appended to an overflow list and re-run by a wider
 // instantiation or by the generic kernel (talco_generic.cu).
 #include "talco_score.cuh"
 #include "twl_device.cuh"
@@ -43,8 +46,47 @@ __device__ __forceinline__ float orderedFloat(int o) { return __int_as_float(o ^
 
 __device__ __forceinline__ void prefetchL1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-template <int NT>
-__global__ void __launch_bounds__(NT) talcoWavefrontKernel(const TalcoArgs a) {
+// Column-pair numerators of the four slots of a thread. MC = 0: any 5x5 matrix, full reference order.
+// MC = 1 ("DNA3Z"): the built-in nucleotide matrix shape (scoring-matrix.cpp:103-112 without --wildcard):
+// S[l][l] = A, S[l][m] = B for |l-m| = 2, C otherwise, and an all-zero N row/column. The N terms of the reference sum
+// are exact zeros and are dropped; every remaining product and sum is evaluated in the reference order.
+template <int MC>
+__device__ __forceinline__ void numerators4(const float (&r)[kSlots][6], const float (&q)[kSlots][6], const TalcoArgs &a,
+                                            float (&num)[kSlots]) {
+    if (MC == 0) {
+#pragma unroll
+        for (int c = 0; c < kSlots; ++c) {
+            float n = 0.0f;
+#pragma unroll
+            for (int l = 0; l < 5; ++l) {
+                const float t0 = __fmul_rn(__fmul_rn(q[c][0], a.scoreNt[l * 5 + 0]), r[c][l]);
+                const float t1 = __fmul_rn(__fmul_rn(q[c][1], a.scoreNt[l * 5 + 1]), r[c][l]);
+                const float t2 = __fmul_rn(__fmul_rn(q[c][2], a.scoreNt[l * 5 + 2]), r[c][l]);
+                const float t3 = __fmul_rn(__fmul_rn(q[c][3], a.scoreNt[l * 5 + 3]), r[c][l]);
+                const float t4 = __fmul_rn(__fmul_rn(q[c][4], a.scoreNt[l * 5 + 4]), r[c][l]);
+                n = __fadd_rn(n, __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(t0, t1), t2), t3), t4));
+            }
+            num[c] = n;
+        }
+    } else {
+        const float A = a.scoreNt[0], B = a.scoreNt[2], C = a.scoreNt[1];
+#pragma unroll
+        for (int c = 0; c < kSlots; ++c) {
+            float qa[4], qb[4], qc[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) { qa[m] = __fmul_rn(q[c][m], A); qb[m] = __fmul_rn(q[c][m], B); qc[m] = __fmul_rn(q[c][m], C); }
+            const float r0 = r[c][0], r1 = r[c][1], r2 = r[c][2], r3 = r[c][3];
+            const float h0 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(qa[0], r0), __fmul_rn(qc[1], r0)), __fmul_rn(qb[2], r0)), __fmul_rn(qc[3], r0));
+            const float h1 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(qc[0], r1), __fmul_rn(qa[1], r1)), __fmul_rn(qc[2], r1)), __fmul_rn(qb[3], r1));
+            const float h2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(qb[0], r2), __fmul_rn(qc[1], r2)), __fmul_rn(qa[2], r2)), __fmul_rn(qc[3], r2));
+            const float h3 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(qc[0], r3), __fmul_rn(qb[1], r3)), __fmul_rn(qc[2], r3)), __fmul_rn(qa[3], r3));
+            num[c] = __fadd_rn(__fadd_rn(__fadd_rn(h0, h1), h2), h3);
+        }
+    }
+}
+
+template <int NT, int MC>
+__global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefrontKernel(const TalcoArgs a) {
     constexpr int W = NT * kSlots;
     constexpr int NW = NT / 32;
     constexpr int PW = 8;
@@ -72,7 +114,9 @@ __global__ void __launch_bounds__(NT) talcoWavefrontKernel(const TalcoArgs a) {
         const float negInf = -static_cast<float>(2.0 * pr.xdrop + 1.0);
         const float xdropF = static_cast<float>(pr.xdrop);
         const float denom = __fmul_rn(pr.refNum, pr.qryNum);
-        const bool unitDenom = (denom == 1.0f);
+        const float rcp = __fdiv_rn(1.0f, denom);
+        // 0: denominator is 1 (no division), 1: reciprocal-based exact division, 2: IEEE divide (mantissa of all ones)
+        const int divMode = (denom == 1.0f) ? 0 : (((__float_as_int(denom) & 0x7fffff) == 0x7fffff) ? 2 : 1);
         const float gapChar = pr.gapChar;
         int refOff = 0, qryOff = 0, tile = 0, outPos = 0, status = 0;
         unsigned long long cells = 0, diagonals = 0;
@@ -92,14 +136,17 @@ __global__ void __launch_bounds__(NT) talcoWavefrontKernel(const TalcoArgs a) {
             // per-slot register state
             float h1[kSlots], i1[kSlots], d1[kSlots], h2[kSlots];      // H,I,D of diagonal k-1 and H of k-2 for the slot's row
             float q[kSlots][6], gOpQ[kSlots], gExQ[kSlots];
-            int rowCur[kSlots];
 #pragma unroll
-            for (int c = 0; c < kSlots; ++c) { h1[c] = i1[c] = d1[c] = h2[c] = -1.0f; rowCur[c] = -1; gOpQ[c] = gExQ[c] = 0.f;
+            for (int c = 0; c < kSlots; ++c) {
+                h1[c] = i1[c] = d1[c] = h2[c] = -1.0f; gOpQ[c] = gExQ[c] = 0.f;
 #pragma unroll
-                for (int t = 0; t < 6; ++t) q[c][t] = 0.f; }
+                for (int t = 0; t < 6; ++t) q[c][t] = 0.f;
+            }
+            int rowBase = -1;                                          // first of the 4 rows this thread currently holds
             float leftHPrev = -1.0f;                                   // H[k-2] of the row below slot 0
 
             int L0 = 0, U0 = 0, L1 = 2, U1 = -2, L2 = 1, U2 = -1;
+            int c0 = 0, c1 = 2, c2 = 1;                                // k%3, (k+2)%3, (k+1)%3
             float maxScore = 0.0f, maxScorePrime = negInf, convScore = 0.0f;
             bool converged = false, stopped = false;
             int convValue = 0, prevConvS = -1, lastK = 0, nStored = 0, error = 0;
@@ -108,21 +155,20 @@ __global__ void __launch_bounds__(NT) talcoWavefrontKernel(const TalcoArgs a) {
             const float *qryTile = qryCols + static_cast<size_t>(qryOff) * PW;
 
             for (int k = 0; k < nDiag; ++k) {
-                const int c0 = k % 3, c1 = (k + 2) % 3, c2 = (k + 1) % 3, g0 = k & 1, g1 = g0 ^ 1;
+                const int g0 = k & 1, g1 = g0 ^ 1;
                 if (L0 >= U0 + 1) { error = 1; break; }
                 const int width = U0 - L0 + 1;
                 if (width > cap) { error = 2; break; }
-                if (width > W) { error = kStatusRetryWide; break; }
+                const int Lb = L0 & ~(kSlots - 1);                     // window base: multiple of 4 so a thread's rows never wrap
+                if (U0 - Lb >= W) { error = kStatusRetryWide; break; }
                 if (k <= marker) nStored = k + 1;
                 cells += static_cast<unsigned long long>(width);
                 diagonals += 1;
                 const float pruneBelow = __fsub_rn(maxScore, xdropF);
 
-                if (tid == 0) {   // warm L1 for the columns the band edges will touch a few diagonals from now
-                    const int jAhead = min(refLen - 1, k - L0 + 12);
-                    const int iAhead = min(qryLen - 1, L0 + W + 8);
-                    prefetchL1(refTile + static_cast<size_t>(jAhead) * PW);
-                    prefetchL1(qryTile + static_cast<size_t>(iAhead) * PW);
+                if (tid == 0) {   // warm L1 for the lines the band edges will touch a few diagonals from now
+                    prefetchL1(refTile + static_cast<size_t>(min(refLen - 1, k - L0 + 12)) * PW);
+                    prefetchL1(qryTile + static_cast<size_t>(min(qryLen - 1, Lb + W + 8)) * PW);
                 }
 
                 // row-neighbour of slot 0: last slot of the previous thread (previous warp through shared memory)
@@ -133,73 +179,116 @@ __global__ void __launch_bounds__(NT) talcoWavefrontKernel(const TalcoArgs a) {
                     nbH = e.x; nbI = e.y;
                 }
 
+                const int iBase = Lb + ((rho0 - Lb) & (W - 1));         // rows iBase .. iBase+3
+                if (iBase != rowBase) {                                // thread re-assigned: fetch its 4 query columns
+                    rowBase = iBase;
+#pragma unroll
+                    for (int c = 0; c < kSlots; ++c) {
+                        const int i = min(iBase + c, qryLen - 1);
+                        const float4 x = __ldg(reinterpret_cast<const float4 *>(qryTile + static_cast<size_t>(i) * PW));
+                        const float4 y = __ldg(reinterpret_cast<const float4 *>(qryTile + static_cast<size_t>(i) * PW) + 1);
+                        q[c][0] = x.x; q[c][1] = x.y; q[c][2] = x.z; q[c][3] = x.w; q[c][4] = y.x; q[c][5] = y.y;
+                        gOpQ[c] = y.z; gExQ[c] = y.w;
+                    }
+                }
+
                 float myMax = negInf;
                 int myLo = 0x7fffffff, myHi = -0x7fffffff;
+                unsigned tbWord = 0, actBits = 0;
+                const bool anyAct = (iBase <= U0) && (iBase + kSlots - 1 >= L0);
                 float nh[kSlots], ni[kSlots], nd[kSlots];
-                unsigned tbWord = 0;
-                unsigned liveBits = 0;
-                int cs[kSlots], ci[kSlots], cd[kSlots];
-
 #pragma unroll
-                for (int c = 0; c < kSlots; ++c) {
-                    const int rho = rho0 + c;
-                    const int i = L0 + ((rho - L0) & (W - 1));
-                    nh[c] = h1[c]; ni[c] = i1[c]; nd[c] = d1[c];
-                    cs[c] = ci[c] = cd[c] = 0;
-                    if (i != rowCur[c]) {                               // slot re-assigned: fetch its query column
-                        rowCur[c] = i;
-                        if (i < qryLen) {
-                            const float4 x = __ldg(reinterpret_cast<const float4 *>(qryTile + static_cast<size_t>(i) * PW));
-                            const float4 y = __ldg(reinterpret_cast<const float4 *>(qryTile + static_cast<size_t>(i) * PW) + 1);
-                            q[c][0] = x.x; q[c][1] = x.y; q[c][2] = x.z; q[c][3] = x.w; q[c][4] = y.x; q[c][5] = y.y;
-                            gOpQ[c] = y.z; gExQ[c] = y.w;
+                for (int c = 0; c < kSlots; ++c) { nh[c] = h1[c]; ni[c] = i1[c]; nd[c] = d1[c]; }
+
+                if (__any_sync(0xffffffffu, anyAct)) {
+                    // the diagonal needs the general match rule only on diagonal 0 and while the band touches the
+                    // first row/column of the first tile (TALCO-XDrop.cpp:369-371, 445-449)
+                    const bool special = (k < 2) || (tile == 0 && (L0 == 0 || U0 == k));
+                    float r[kSlots][6], gOpR[kSlots], gExR[kSlots], num[kSlots];
+                    bool gap = false;
+#pragma unroll
+                    for (int c = 0; c < kSlots; ++c) {
+                        const int j = min(max(k - (iBase + c), 0), refLen - 1);
+                        const float4 x = __ldg(reinterpret_cast<const float4 *>(refTile + static_cast<size_t>(j) * PW));
+                        const float4 y = __ldg(reinterpret_cast<const float4 *>(refTile + static_cast<size_t>(j) * PW) + 1);
+                        r[c][0] = x.x; r[c][1] = x.y; r[c][2] = x.z; r[c][3] = x.w; r[c][4] = y.x; r[c][5] = y.y;
+                        gOpR[c] = y.z; gExR[c] = y.w;
+                        gap = gap || (y.y != 0.0f) || (q[c][5] != 0.0f);
+                    }
+                    numerators4<MC>(r, q, a, num);
+                    if (__any_sync(0xffffffffu, gap)) {                 // gap-character terms (exact zeros otherwise)
+#pragma unroll
+                        for (int c = 0; c < kSlots; ++c) {
+                            float n = num[c];
+#pragma unroll
+                            for (int l = 0; l < 5; ++l) n = __fmaf_rn(__fmul_rn(r[c][l], q[c][5]), gapChar, n);
+#pragma unroll
+                            for (int m = 0; m < 5; ++m) n = __fmaf_rn(__fmul_rn(r[c][5], q[c][m]), gapChar, n);
+                            num[c] = n;
                         }
                     }
-                    if (i <= U0) {
-                        const int j = k - i;
+                    if (divMode == 1) {
+#pragma unroll
+                        for (int c = 0; c < kSlots; ++c) num[c] = exactDiv(num[c], denom, rcp);
+                    } else if (divMode == 2) {
+#pragma unroll
+                        for (int c = 0; c < kSlots; ++c) num[c] = __fdiv_rn(num[c], denom);
+                    }
+
+#pragma unroll
+                    for (int c = 0; c < kSlots; ++c) {
+                        const int i = iBase + c;
+                        const bool act = (i >= L0) && (i <= U0);
                         const float leftH = (c == 0) ? nbH : h1[(c + kSlots - 1) % kSlots];
                         const float leftI = (c == 0) ? nbI : i1[(c + kSlots - 1) % kSlots];
                         const float diagH = (c == 0) ? leftHPrev : h2[(c + kSlots - 1) % kSlots];
-                        const float4 x = __ldg(reinterpret_cast<const float4 *>(refTile + static_cast<size_t>(j) * PW));
-                        const float4 y = __ldg(reinterpret_cast<const float4 *>(refTile + static_cast<size_t>(j) * PW) + 1);
-                        const float r[6] = {x.x, x.y, x.z, x.w, y.x, y.y};
-                        const float gOpR = y.z, gExR = y.w;
-                        const bool upIn = (i <= U1);                    // i >= L0 >= L1 always
-                        const bool leftIn = (i > L1);                   // i-1 <= U0-1 <= U1 always
+                        const bool upIn = (i <= U1);                    // i >= L0 >= L1 for live cells
+                        const bool leftIn = (i > L1);                   // i-1 <= U0-1 <= U1 for live cells
                         const bool diagIn = (i - 1 >= L2) && (i - 1 <= U2);
-                        const bool onEdge0 = (tile == 0) && (i == 0 || j == 0);
-                        float match = negInf;
-                        if (k == 0 || diagIn || onEdge0) {
-                            const float num = numeratorNt(r, q[c], a.scoreNt, gapChar);
-                            const float sim = unitDenom ? num : __fdiv_rn(num, denom);
+                        float match;
+                        if (!special) {
+                            match = diagIn ? __fadd_rn(diagH, num[c]) : negInf;
+                        } else {
+                            const int j = k - i;
+                            const bool onEdge0 = (tile == 0) && (i == 0 || j == 0);
+                            match = negInf;
                             if (onEdge0) {
-                                if (i == 0 && j == 0) match = sim;
-                                else match = __fmaf_rn(a.gapExtend, static_cast<float>(max(0, max(refOff + j, qryOff + i) - 1)), __fadd_rn(sim, a.gapOpen));
-                            } else if (!diagIn) match = sim;           // k == 0
-                            else match = __fadd_rn(diagH, sim);
+                                if (i == 0 && j == 0) match = num[c];
+                                else match = __fmaf_rn(a.gapExtend, static_cast<float>(max(0, max(refOff + j, qryOff + i) - 1)), __fadd_rn(num[c], a.gapOpen));
+                            } else if (k == 0) match = num[c];
+                            else if (diagIn) match = __fadd_rn(diagH, num[c]);
                         }
-                        const float delOpen = upIn ? __fadd_rn(h1[c], gOpR) : negInf;
-                        const float delExt = upIn ? __fadd_rn(d1[c], gExR) : negInf;
+                        const float delOpen = upIn ? __fadd_rn(h1[c], gOpR[c]) : negInf;
+                        const float delExt = upIn ? __fadd_rn(d1[c], gExR[c]) : negInf;
                         const float insOpen = leftIn ? __fadd_rn(leftH, gOpQ[c]) : negInf;
                         const float insExt = leftIn ? __fadd_rn(leftI, gExQ[c]) : negInf;
                         const bool insFromIns = insExt >= insOpen, delFromDel = delExt >= delOpen;
-                        const float insBest = insFromIns ? insExt : insOpen, delBest = delFromDel ? delExt : delOpen;
-                        int ptr;
-                        float s;
-                        if (match >= insBest) {
-                            if (match >= delBest) { s = match; ptr = 0; }
-                            else { s = delBest; ptr = 2; }
-                        } else if (insBest > delBest) { s = insBest; ptr = 1; }
-                        else { s = delBest; ptr = 2; }
+                        const float insBest = fmaxf(insExt, insOpen), delBest = fmaxf(delExt, delOpen);
+                        const bool mGeI = match >= insBest, mGeD = match >= delBest, iGtD = insBest > delBest;
+                        const int ptr = (mGeI && mGeD) ? 0 : ((!mGeI && iGtD) ? 1 : 2);
+                        float s = fmaxf(match, fmaxf(insBest, delBest));
                         if (s < pruneBelow) s = negInf;
+                        s = act ? s : negInf;
                         nh[c] = s; ni[c] = insBest; nd[c] = delBest;
                         myMax = fmaxf(myMax, s);
                         if (s > negInf) { myLo = min(myLo, i); myHi = max(myHi, i); }
-                        liveBits |= 1u << c;
+                        actBits |= (act ? 1u : 0u) << c;
                         tbWord |= static_cast<unsigned>(ptr | (insFromIns ? 4 : 0) | (delFromDel ? 8 : 0)) << (8 * c);
+                    }
+                    if (k <= marker && actBits) *reinterpret_cast<unsigned *>(tb + static_cast<size_t>(k) * W + rho0) = tbWord;
+                }
 
-                        if (k >= marker - 1) {                          // convergence pointers, reference indexing
+                int cs[kSlots], ci[kSlots], cd[kSlots];
+#pragma unroll
+                for (int c = 0; c < kSlots; ++c) cs[c] = ci[c] = cd[c] = 0;
+                if (k >= marker - 1) {                                  // convergence pointers, reference indexing (:520-547)
+#pragma unroll
+                    for (int c = 0; c < kSlots; ++c) {
+                        if (actBits & (1u << c)) {
+                            const int i = iBase + c;
                             const int off = i - L0, offDiag = i - 1 - L2, offUp = i - L1, offLeft = offUp - 1;
+                            const unsigned nib = (tbWord >> (8 * c)) & 15u;
+                            const int ptr = nib & 3;
                             if (k == marker - 1) {
                                 cs[c] = (3 << 16) | (i & 0xFFFF);
                                 sCS[c0][off] = cs[c];
@@ -208,9 +297,9 @@ __global__ void __launch_bounds__(NT) talcoWavefrontKernel(const TalcoArgs a) {
                                 sCS[c0][off] = cs[c]; sCI[g0][off] = ci[c]; sCD[g0][off] = cd[c];
                             } else {
                                 int vi, vd;
-                                if (insFromIns) vi = (offLeft >= 0) ? sCI[g1][offLeft] : kInsBoundary;
+                                if (nib & 4u) vi = (offLeft >= 0) ? sCI[g1][offLeft] : kInsBoundary;
                                 else { const int v = (offLeft >= 0) ? sCS[c1][offLeft] : -1; vi = (v != -1) ? v : kInsBoundary; }
-                                if (delFromDel) vd = (offUp >= 0) ? sCD[g1][offUp] : kDelBoundary;
+                                if (nib & 8u) vd = (offUp >= 0) ? sCD[g1][offUp] : kDelBoundary;
                                 else { const int v = (offUp >= 0) ? sCS[c1][offUp] : -1; vd = (v != -1) ? v : kDelBoundary; }
                                 const int vs = (ptr == 0) ? ((offDiag >= 0) ? sCS[c2][offDiag] : -1) : ((ptr == 1) ? vi : vd);
                                 ci[c] = vi; cd[c] = vd; cs[c] = vs;
@@ -219,7 +308,6 @@ __global__ void __launch_bounds__(NT) talcoWavefrontKernel(const TalcoArgs a) {
                         }
                     }
                 }
-                if (k <= marker && liveBits) *reinterpret_cast<unsigned *>(tb + static_cast<size_t>(k) * W + rho0) = tbWord;
 
                 // rotate the register wavefront
                 leftHPrev = nbH;
@@ -248,12 +336,10 @@ __global__ void __launch_bounds__(NT) talcoWavefrontKernel(const TalcoArgs a) {
                     unsigned bad = 0;
 #pragma unroll
                     for (int c = 0; c < kSlots; ++c) {
-                        if (liveBits & (1u << c)) {
-                            const int i = rowCur[c];
-                            if (i > newL && i <= newU) {
-                                if (ci[c] != vI || cd[c] != vD) bad |= 1u;
-                                if (cs[c] != vS) bad |= 2u;
-                            }
+                        const int i = iBase + c;
+                        if ((actBits & (1u << c)) && i > newL && i <= newU) {
+                            if (ci[c] != vI || cd[c] != vD) bad |= 1u;
+                            if (cs[c] != vS) bad |= 2u;
                         }
                     }
                     if (bad) atomicAnd(&sh.convMask[c0], ~bad);
@@ -272,6 +358,7 @@ __global__ void __launch_bounds__(NT) talcoWavefrontKernel(const TalcoArgs a) {
                 const int nextL = max(newL, max(0, k + 2 - refLen));
                 const int nextU = min(qryLen - 1, newU + 1);
                 L2 = L1; U2 = U1; L1 = L0; U1 = U0; L0 = nextL; U0 = nextU;
+                { const int t = c1; c1 = c0; c0 = c2; c2 = t; }
                 maxScore = (maxScorePrime < 0.0f) ? 0.0f : maxScorePrime;
                 lastK = k;
                 if (converged && maxScore > convScore) { stopped = true; break; }
@@ -362,26 +449,61 @@ __global__ void __launch_bounds__(NT) talcoWavefrontKernel(const TalcoArgs a) {
     }
 }
 
-int wavefrontBandCapacity(int threads) { return threads * kSlots; }
+// The wavefront kernels hold bands of up to W-3 cells (the window base is rounded down to a multiple of 4).
+int wavefrontBandCapacity(int threads) { return threads * kSlots - (kSlots - 1); }
+int wavefrontWindow(int threads) { return threads * kSlots; }
 
-cudaError_t launchTalcoWavefront(int threads, const TalcoArgs &args, int grid, cudaStream_t stream) {
+// 1 when the matrix has the built-in nucleotide shape with an all-zero N row/column (see numerators4).
+int nucleotideMatrixClass(const float *s) {
+    const float A = s[0], B = s[2], C = s[1];
+    for (int l = 0; l < 5; ++l)
+        for (int m = 0; m < 5; ++m) {
+            const float want = (l == 4 || m == 4) ? 0.0f : ((l == m) ? A : ((l - m == 2 || m - l == 2) ? B : C));
+            if (s[l * 5 + m] != want) return 0;
+        }
+    return 1;
+}
+
+// Self-test of exactDiv against the IEEE divide (twl_selftest_division): counts the operand pairs on which they differ.
+__global__ void divSelfTestKernel(const float *num, const float *den, int n, int *mismatches) {
+    int bad = 0;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const float d = den[t];
+        const float viaRcp = exactDiv(num[t], d, __fdiv_rn(1.0f, d));
+        const float ieee = __fdiv_rn(num[t], d);
+        if (__float_as_int(viaRcp) != __float_as_int(ieee) && !((__float_as_int(d) & 0x7fffff) == 0x7fffff)) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+cudaError_t launchDivSelfTest(const float *num, const float *den, int n, int *mismatches, cudaStream_t stream) {
+    divSelfTestKernel<<<296, 256, 0, stream>>>(num, den, n, mismatches);
+    return cudaGetLastError();
+}
+
+template <int MC>
+static cudaError_t launchMc(int threads, const TalcoArgs &args, int grid, cudaStream_t stream) {
     switch (threads) {
-    case 64: talcoWavefrontKernel<64><<<grid, 64, 0, stream>>>(args); break;
-    case 128: talcoWavefrontKernel<128><<<grid, 128, 0, stream>>>(args); break;
-    case 256: talcoWavefrontKernel<256><<<grid, 256, 0, stream>>>(args); break;
+    case 64: talcoWavefrontKernel<64, MC><<<grid, 64, 0, stream>>>(args); break;
+    case 128: talcoWavefrontKernel<128, MC><<<grid, 128, 0, stream>>>(args); break;
+    case 256: talcoWavefrontKernel<256, MC><<<grid, 256, 0, stream>>>(args); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }
 
-int wavefrontMaxCtasPerSm(int threads) {
+cudaError_t launchTalcoWavefront(int threads, int matClass, const TalcoArgs &args, int grid, cudaStream_t stream) {
+    return matClass == 1 ? launchMc<1>(threads, args, grid, stream) : launchMc<0>(threads, args, grid, stream);
+}
+
+int wavefrontMaxCtasPerSm(int threads, int matClass) {
     int n = 0;
-    switch (threads) {
-    case 64: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, talcoWavefrontKernel<64>, 64, 0); break;
-    case 128: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, talcoWavefrontKernel<128>, 128, 0); break;
-    case 256: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, talcoWavefrontKernel<256>, 256, 0); break;
-    default: break;
+#define TWL_OCC(NT_, MC_) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, talcoWavefrontKernel<NT_, MC_>, NT_, 0)
+    if (matClass == 1) {
+        if (threads == 64) TWL_OCC(64, 1); else if (threads == 128) TWL_OCC(128, 1); else if (threads == 256) TWL_OCC(256, 1);
+    } else {
+        if (threads == 64) TWL_OCC(64, 0); else if (threads == 128) TWL_OCC(128, 0); else if (threads == 256) TWL_OCC(256, 0);
     }
+#undef TWL_OCC
     return n;
 }
 

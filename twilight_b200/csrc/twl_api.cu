@@ -17,8 +17,11 @@ size_t genericStateWords(int stateCap);
 cudaError_t launchTalcoGeneric(int P, bool globalState, const TalcoArgs &args, int grid, size_t dynSmemBytes, cudaStream_t stream);
 int genericThreads();
 int wavefrontBandCapacity(int threads);
-cudaError_t launchTalcoWavefront(int threads, const TalcoArgs &args, int grid, cudaStream_t stream);
-int wavefrontMaxCtasPerSm(int threads);
+int wavefrontWindow(int threads);
+int nucleotideMatrixClass(const float *score5x5);
+cudaError_t launchTalcoWavefront(int threads, int matClass, const TalcoArgs &args, int grid, cudaStream_t stream);
+int wavefrontMaxCtasPerSm(int threads, int matClass);
+cudaError_t launchDivSelfTest(const float *num, const float *den, int n, int *mismatches, cudaStream_t stream);
 } // namespace twl
 
 namespace {
@@ -306,13 +309,14 @@ int twl_batch_run(twl_ctx *ctx) {
     //   nucleotide: wavefront<128> (band <= 512) -> wavefront<256> (band <= 1024) -> generic/global state (any band)
     //   protein   : generic/shared state (band <= 1020)                            -> generic/global state
     struct Stage { int kind; int threads; int cap; int grid; size_t tbStride; };   // kind 0 wavefront, 1 generic smem, 2 generic global
+    const int matClass = nucleotide ? twl::nucleotideMatrixClass(ctx->hScore.data()) : 0;
     std::vector<Stage> stages;
     auto tbRows = [&](int w) { return (static_cast<size_t>(marker + 1) * w + 255) & ~static_cast<size_t>(255); };
     if (nucleotide) {
         for (int threads : {128, 256}) {
             const int cap = twl::wavefrontBandCapacity(threads);
-            const int perSm = std::max(1, twl::wavefrontMaxCtasPerSm(threads));
-            stages.push_back({0, threads, cap, std::min(n, ctx->smCount * perSm), tbRows(cap)});
+            const int perSm = std::max(1, twl::wavefrontMaxCtasPerSm(threads, matClass));
+            stages.push_back({0, threads, cap, std::min(n, ctx->smCount * perSm), tbRows(twl::wavefrontWindow(threads))});
             if (wideCap <= cap) break;
         }
     } else {
@@ -361,7 +365,7 @@ int twl_batch_run(twl_ctx *ctx) {
         a.stateCap = st.cap;
         a.stateScratch = (st.kind == 2) ? ctx->dState.ptr : nullptr;
         a.stateStride = (st.kind == 2) ? twl::genericStateWords(st.cap) : 0;
-        if (st.kind == 0) TWL_CUDA(ctx, twl::launchTalcoWavefront(st.threads, a, st.grid, ctx->stream));
+        if (st.kind == 0) TWL_CUDA(ctx, twl::launchTalcoWavefront(st.threads, matClass, a, st.grid, ctx->stream));
         else TWL_CUDA(ctx, twl::launchTalcoGeneric(ctx->P, st.kind == 2, a, st.grid, st.kind == 1 ? twl::genericStateWords(st.cap) * sizeof(float) : 0, ctx->stream));
         ctx->lastLaunches += 1;
     }
@@ -412,6 +416,24 @@ int twl_set_option(twl_ctx *ctx, const char *name, int value) {
     if (!ctx || !name) return TWL_E_ARG;
     if (std::strcmp(name, "force_generic") == 0) { ctx->forceGeneric = value != 0; return TWL_OK; }
     return fail(ctx, TWL_E_ARG, std::string("twl_set_option: unknown option ") + name);
+}
+
+int twl_selftest_division(twl_ctx *ctx, const float *num, const float *den, int n, int *mismatches) {
+    if (!ctx || !num || !den || !mismatches || n < 0) return TWL_E_ARG;
+    cudaSetDevice(ctx->device);
+    float *dn = nullptr, *dd = nullptr;
+    int *dm = nullptr;
+    TWL_CUDA(ctx, cudaMalloc(&dn, sizeof(float) * std::max(n, 1)));
+    TWL_CUDA(ctx, cudaMalloc(&dd, sizeof(float) * std::max(n, 1)));
+    TWL_CUDA(ctx, cudaMalloc(&dm, sizeof(int)));
+    TWL_CUDA(ctx, cudaMemcpyAsync(dn, num, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
+    TWL_CUDA(ctx, cudaMemcpyAsync(dd, den, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
+    TWL_CUDA(ctx, cudaMemsetAsync(dm, 0, sizeof(int), ctx->stream));
+    TWL_CUDA(ctx, twl::launchDivSelfTest(dn, dd, n, dm, ctx->stream));
+    TWL_CUDA(ctx, cudaMemcpyAsync(mismatches, dm, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(dn); cudaFree(dd); cudaFree(dm);
+    return TWL_OK;
 }
 
 float twl_last_kernel_ms(const twl_ctx *ctx) {
