@@ -146,24 +146,26 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
             float leftHPrev = -1.0f;                                   // H[k-2] of the row below slot 0
 
             int L0 = 0, U0 = 0, L1 = 2, U1 = -2, L2 = 1, U2 = -1;
-            int c0 = 0, c1 = 2, c2 = 1;                                // k%3, (k+2)%3, (k+1)%3
             float maxScore = 0.0f, maxScorePrime = negInf, convScore = 0.0f;
             bool converged = false, stopped = false;
-            int convValue = 0, prevConvS = -1, lastK = 0, nStored = 0, error = 0;
+            int convValue = 0, prevConvS = -1, lastK = 0, error = 0;
+            unsigned tileCells = 0;
             const int nDiag = refLen + qryLen - 1;
             const float *refTile = refCols + static_cast<size_t>(refOff) * PW;
             const float *qryTile = qryCols + static_cast<size_t>(qryOff) * PW;
+            const int prevWarp = (warp + NW - 1) % NW;
+            int g0 = 1;
 
             for (int k = 0; k < nDiag; ++k) {
-                const int g0 = k & 1, g1 = g0 ^ 1;
-                if (L0 >= U0 + 1) { error = 1; break; }
+                g0 ^= 1;
+                const int g1 = g0 ^ 1;
                 const int width = U0 - L0 + 1;
-                if (width > cap) { error = 2; break; }
                 const int Lb = L0 & ~(kSlots - 1);                     // window base: multiple of 4 so a thread's rows never wrap
-                if (U0 - Lb >= W) { error = kStatusRetryWide; break; }
-                if (k <= marker) nStored = k + 1;
-                cells += static_cast<unsigned long long>(width);
-                diagonals += 1;
+                if (width <= 0 || width > cap || U0 - Lb >= W) {       // :323-338, plus this kernel's own capacity
+                    error = (width <= 0) ? 1 : ((width > cap) ? 2 : kStatusRetryWide);
+                    break;
+                }
+                tileCells += static_cast<unsigned>(width);
                 const float pruneBelow = __fsub_rn(maxScore, xdropF);
 
                 if (tid == 0) {   // warm L1 for the lines the band edges will touch a few diagonals from now
@@ -174,9 +176,10 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
                 // row-neighbour of slot 0: last slot of the previous thread (previous warp through shared memory)
                 float nbH = __shfl_up_sync(0xffffffffu, h1[kSlots - 1], 1);
                 float nbI = __shfl_up_sync(0xffffffffu, i1[kSlots - 1], 1);
-                if (lane == 0) {
-                    const float2 e = sh.edge[g1][(warp + NW - 1) % NW];
-                    nbH = e.x; nbI = e.y;
+                {
+                    const float2 e = sh.edge[g1][prevWarp];
+                    nbH = (lane == 0) ? e.x : nbH;
+                    nbI = (lane == 0) ? e.y : nbI;
                 }
 
                 const int iBase = Lb + ((rho0 - Lb) & (W - 1));         // rows iBase .. iBase+3
@@ -196,16 +199,10 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
                 int myLo = 0x7fffffff, myHi = -0x7fffffff;
                 unsigned tbWord = 0, actBits = 0;
                 const bool anyAct = (iBase <= U0) && (iBase + kSlots - 1 >= L0);
-                float nh[kSlots], ni[kSlots], nd[kSlots];
-#pragma unroll
-                for (int c = 0; c < kSlots; ++c) { nh[c] = h1[c]; ni[c] = i1[c]; nd[c] = d1[c]; }
 
                 if (__any_sync(0xffffffffu, anyAct)) {
-                    // the diagonal needs the general match rule only on diagonal 0 and while the band touches the
-                    // first row/column of the first tile (TALCO-XDrop.cpp:369-371, 445-449)
-                    const bool special = (k < 2) || (tile == 0 && (L0 == 0 || U0 == k));
                     float r[kSlots][6], gOpR[kSlots], gExR[kSlots], num[kSlots];
-                    bool gap = false;
+                    bool gapQ = false, gapR = false;
 #pragma unroll
                     for (int c = 0; c < kSlots; ++c) {
                         const int j = min(max(k - (iBase + c), 0), refLen - 1);
@@ -213,19 +210,23 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
                         const float4 y = __ldg(reinterpret_cast<const float4 *>(refTile + static_cast<size_t>(j) * PW) + 1);
                         r[c][0] = x.x; r[c][1] = x.y; r[c][2] = x.z; r[c][3] = x.w; r[c][4] = y.x; r[c][5] = y.y;
                         gOpR[c] = y.z; gExR[c] = y.w;
-                        gap = gap || (y.y != 0.0f) || (q[c][5] != 0.0f);
+                        gapR = gapR || (y.y != 0.0f);
+                        gapQ = gapQ || (q[c][5] != 0.0f);
                     }
                     numerators4<MC>(r, q, a, num);
-                    if (__any_sync(0xffffffffu, gap)) {                 // gap-character terms (exact zeros otherwise)
+                    // gap-character terms (TALCO-XDrop.cpp:393-394): each loop adds exact zeros unless the query (resp.
+                    // reference) column holds gaps, so it is skipped when no lane of the warp needs it
+                    if (__any_sync(0xffffffffu, gapQ)) {
 #pragma unroll
-                        for (int c = 0; c < kSlots; ++c) {
-                            float n = num[c];
+                        for (int c = 0; c < kSlots; ++c)
 #pragma unroll
-                            for (int l = 0; l < 5; ++l) n = __fmaf_rn(__fmul_rn(r[c][l], q[c][5]), gapChar, n);
+                            for (int l = 0; l < 5; ++l) num[c] = __fmaf_rn(__fmul_rn(r[c][l], q[c][5]), gapChar, num[c]);
+                    }
+                    if (__any_sync(0xffffffffu, gapR)) {
 #pragma unroll
-                            for (int m = 0; m < 5; ++m) n = __fmaf_rn(__fmul_rn(r[c][5], q[c][m]), gapChar, n);
-                            num[c] = n;
-                        }
+                        for (int c = 0; c < kSlots; ++c)
+#pragma unroll
+                            for (int m = 0; m < 5; ++m) num[c] = __fmaf_rn(__fmul_rn(r[c][5], q[c][m]), gapChar, num[c]);
                     }
                     if (divMode == 1) {
 #pragma unroll
@@ -235,53 +236,68 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
                         for (int c = 0; c < kSlots; ++c) num[c] = __fdiv_rn(num[c], denom);
                     }
 
+                    // match candidates: H[k-2][i-1] + sim when the diagonal neighbour is inside its band ...
+                    float match[kSlots];
 #pragma unroll
                     for (int c = 0; c < kSlots; ++c) {
                         const int i = iBase + c;
+                        const float diagH = (c == 0) ? leftHPrev : h2[c - 1 < 0 ? 0 : c - 1];
+                        const bool diagIn = (i - 1 >= L2) && (i - 1 <= U2);
+                        match[c] = diagIn ? __fadd_rn(diagH, num[c]) : negInf;
+                    }
+                    // ... except on diagonal 0 and while the band touches the first row/column of the first tile
+                    // (TALCO-XDrop.cpp:369-371, 445-449)
+                    if (k == 0 || (tile == 0 && (L0 == 0 || U0 == k))) {
+#pragma unroll
+                        for (int c = 0; c < kSlots; ++c) {
+                            const int i = iBase + c, j = k - i;
+                            if (tile == 0 && (i == 0 || j == 0)) {
+                                if (i == 0 && j == 0) match[c] = num[c];
+                                else match[c] = __fmaf_rn(a.gapExtend, static_cast<float>(max(0, max(refOff + j, qryOff + i) - 1)), __fadd_rn(num[c], a.gapOpen));
+                            } else if (k == 0) match[c] = num[c];
+                        }
+                    }
+
+                    // recurrences, highest slot first so every slot still sees its neighbour's previous-diagonal values
+#pragma unroll
+                    for (int c = kSlots - 1; c >= 0; --c) {
+                        const int i = iBase + c;
                         const bool act = (i >= L0) && (i <= U0);
-                        const float leftH = (c == 0) ? nbH : h1[(c + kSlots - 1) % kSlots];
-                        const float leftI = (c == 0) ? nbI : i1[(c + kSlots - 1) % kSlots];
-                        const float diagH = (c == 0) ? leftHPrev : h2[(c + kSlots - 1) % kSlots];
+                        const float leftH = (c == 0) ? nbH : h1[c - 1 < 0 ? 0 : c - 1];
+                        const float leftI = (c == 0) ? nbI : i1[c - 1 < 0 ? 0 : c - 1];
                         const bool upIn = (i <= U1);                    // i >= L0 >= L1 for live cells
                         const bool leftIn = (i > L1);                   // i-1 <= U0-1 <= U1 for live cells
-                        const bool diagIn = (i - 1 >= L2) && (i - 1 <= U2);
-                        float match;
-                        if (!special) {
-                            match = diagIn ? __fadd_rn(diagH, num[c]) : negInf;
-                        } else {
-                            const int j = k - i;
-                            const bool onEdge0 = (tile == 0) && (i == 0 || j == 0);
-                            match = negInf;
-                            if (onEdge0) {
-                                if (i == 0 && j == 0) match = num[c];
-                                else match = __fmaf_rn(a.gapExtend, static_cast<float>(max(0, max(refOff + j, qryOff + i) - 1)), __fadd_rn(num[c], a.gapOpen));
-                            } else if (k == 0) match = num[c];
-                            else if (diagIn) match = __fadd_rn(diagH, num[c]);
-                        }
                         const float delOpen = upIn ? __fadd_rn(h1[c], gOpR[c]) : negInf;
                         const float delExt = upIn ? __fadd_rn(d1[c], gExR[c]) : negInf;
                         const float insOpen = leftIn ? __fadd_rn(leftH, gOpQ[c]) : negInf;
                         const float insExt = leftIn ? __fadd_rn(leftI, gExQ[c]) : negInf;
                         const bool insFromIns = insExt >= insOpen, delFromDel = delExt >= delOpen;
                         const float insBest = fmaxf(insExt, insOpen), delBest = fmaxf(delExt, delOpen);
-                        const bool mGeI = match >= insBest, mGeD = match >= delBest, iGtD = insBest > delBest;
-                        const int ptr = (mGeI && mGeD) ? 0 : ((!mGeI && iGtD) ? 1 : 2);
-                        float s = fmaxf(match, fmaxf(insBest, delBest));
-                        if (s < pruneBelow) s = negInf;
-                        s = act ? s : negInf;
-                        nh[c] = s; ni[c] = insBest; nd[c] = delBest;
+                        const bool mGeI = match[c] >= insBest, mGeD = match[c] >= delBest, iGtD = insBest > delBest;
+                        const unsigned ptr = (mGeI && mGeD) ? 0u : ((!mGeI && iGtD) ? 1u : 2u);
+                        float s = fmaxf(match[c], fmaxf(insBest, delBest));
+                        s = (s < pruneBelow || !act) ? negInf : s;
+                        h2[c] = h1[c]; h1[c] = s; i1[c] = insBest; d1[c] = delBest;
                         myMax = fmaxf(myMax, s);
-                        if (s > negInf) { myLo = min(myLo, i); myHi = max(myHi, i); }
+                        const bool alive = s > negInf;
+                        myLo = alive ? i : myLo;                        // slots run downwards: the last hit is the lowest row
+                        myHi = (alive && myHi < 0) ? i : myHi;          // the first hit is the highest row
                         actBits |= (act ? 1u : 0u) << c;
-                        tbWord |= static_cast<unsigned>(ptr | (insFromIns ? 4 : 0) | (delFromDel ? 8 : 0)) << (8 * c);
+                        tbWord |= (ptr | (insFromIns ? 4u : 0u) | (delFromDel ? 8u : 0u)) << (8 * c);
                     }
                     if (k <= marker && actBits) *reinterpret_cast<unsigned *>(tb + static_cast<size_t>(k) * W + rho0) = tbWord;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < kSlots; ++c) h2[c] = h1[c];
                 }
+                leftHPrev = nbH;
 
                 int cs[kSlots], ci[kSlots], cd[kSlots];
 #pragma unroll
                 for (int c = 0; c < kSlots; ++c) cs[c] = ci[c] = cd[c] = 0;
+                const int c0 = k % 3;
                 if (k >= marker - 1) {                                  // convergence pointers, reference indexing (:520-547)
+                    const int c1 = (c0 + 2) % 3, c2 = (c0 + 1) % 3;
 #pragma unroll
                     for (int c = 0; c < kSlots; ++c) {
                         if (actBits & (1u << c)) {
@@ -309,11 +325,6 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
                     }
                 }
 
-                // rotate the register wavefront
-                leftHPrev = nbH;
-#pragma unroll
-                for (int c = 0; c < kSlots; ++c) { h2[c] = h1[c]; h1[c] = nh[c]; i1[c] = ni[c]; d1[c] = nd[c]; }
-
                 // one barrier per diagonal: publish the warp's edge values and its reduction
                 const int wMax = __reduce_max_sync(0xffffffffu, orderedInt(myMax));
                 const int wLo = __reduce_min_sync(0xffffffffu, myLo);
@@ -331,6 +342,7 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
                 maxScorePrime = fmaxf(maxScorePrime, orderedFloat(oMax));
 
                 if (!converged && k >= marker && k < nDiag - 1) {       // :585-595
+                    const int c2 = (c0 + 1) % 3;
                     const int start = newL - L0;
                     const int vI = sCI[g0][start], vD = sCD[g0][start], vS = sCS[c0][start];
                     unsigned bad = 0;
@@ -355,14 +367,16 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
                     prevConvS = cS;
                 }
 
-                const int nextL = max(newL, max(0, k + 2 - refLen));
-                const int nextU = min(qryLen - 1, newU + 1);
-                L2 = L1; U2 = U1; L1 = L0; U1 = U0; L0 = nextL; U0 = nextU;
-                { const int t = c1; c1 = c0; c0 = c2; c2 = t; }
+                L2 = L1; U2 = U1; L1 = L0; U1 = U0;
+                L0 = max(newL, max(0, k + 2 - refLen));
+                U0 = min(qryLen - 1, newU + 1);
                 maxScore = (maxScorePrime < 0.0f) ? 0.0f : maxScorePrime;
                 lastK = k;
                 if (converged && maxScore > convScore) { stopped = true; break; }
             }
+            cells += tileCells;
+            diagonals += static_cast<unsigned long long>(lastK + 1);
+            const int nStored = min(lastK, marker) + 1;
 
             if (error) { status = error; break; }
 
