@@ -24,18 +24,19 @@ template <int P>
 struct ColLoad;
 template <>
 struct ColLoad<6> {
-    // one packed column = 2 x float4: (c0 c1 c2 c3) (c4 c5 gapOpen gapExtend)
-    static __device__ __forceinline__ void load(const float *p, float (&c)[6], float &gOp, float &gEx) {
-        const float4 a = __ldg(reinterpret_cast<const float4 *>(p));
-        const float4 b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+    // de-interleaved nucleotide layout (twl_device.cuh): X = (c0 c1 c2 c3), Y = (c4 c5 gapOpen gapExtend)
+    static __device__ __forceinline__ void load(const float *side, int n4, int j, float (&c)[6], float &gOp, float &gEx) {
+        const float4 *v = reinterpret_cast<const float4 *>(side) + ntColIndex(j, n4);
+        const float4 a = __ldg(v);
+        const float4 b = __ldg(v + 4 * static_cast<long long>(n4));
         c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y;
         gOp = b.z; gEx = b.w;
     }
 };
 template <>
 struct ColLoad<22> {
-    static __device__ __forceinline__ void load(const float *p, float (&c)[22], float &gOp, float &gEx) {
-        const float4 *v = reinterpret_cast<const float4 *>(p);
+    static __device__ __forceinline__ void load(const float *side, int /*n4*/, int j, float (&c)[22], float &gOp, float &gEx) {
+        const float4 *v = reinterpret_cast<const float4 *>(side + static_cast<size_t>(j) * 24);
 #pragma unroll
         for (int t = 0; t < 5; ++t) {
             const float4 a = __ldg(v + t);
@@ -73,7 +74,6 @@ struct TileShared {
 
 template <int P, bool GLOBAL_STATE>
 __global__ void __launch_bounds__(kGenThreads) talcoGenericKernel(const TalcoArgs a) {
-    constexpr int PW = P + 2;
     constexpr int MS = (P - 1) * (P - 1);
     extern __shared__ __align__(16) unsigned char dynSmem[];
     __shared__ TileShared sh;
@@ -156,8 +156,8 @@ __global__ void __launch_bounds__(kGenThreads) talcoGenericKernel(const TalcoArg
                     const int off = i - L0, offDiag = i - 1 - L2, offUp = i - L1, offLeft = offUp - 1;
                     float match = negInf, insOpen = negInf, insExt = negInf, delOpen = negInf, delExt = negInf;
                     float r[P], q[P], gOpR, gExR, gOpQ, gExQ;
-                    ColLoad<P>::load(refCols + static_cast<size_t>(refOff + j) * PW, r, gOpR, gExR);
-                    ColLoad<P>::load(qryCols + static_cast<size_t>(qryOff + i) * PW, q, gOpQ, gExQ);
+                    ColLoad<P>::load(refCols, pr.refN4, refOff + j, r, gOpR, gExR);
+                    ColLoad<P>::load(qryCols, pr.qryN4, qryOff + i, q, gOpQ, gExQ);
                     const bool diagIn = offDiag >= 0 && offDiag <= U2 - L2;
                     const bool onEdge0 = (tile == 0) && (i == 0 || j == 0);
                     if (k == 0 || diagIn || onEdge0) {

@@ -89,7 +89,6 @@ template <int NT, int MC>
 __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefrontKernel(const TalcoArgs a) {
     constexpr int W = NT * kSlots;
     constexpr int NW = NT / 32;
-    constexpr int PW = 8;
     constexpr int CW = W + 4;                       // convergence arrays, reference indexing (row - L[k]) plus padding
     __shared__ WaveShared sh;
     __shared__ int sCS[3][CW], sCI[2][CW], sCD[2][CW];
@@ -151,8 +150,8 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
             int convValue = 0, prevConvS = -1, lastK = 0, error = 0;
             unsigned tileCells = 0;
             const int nDiag = refLen + qryLen - 1;
-            const float *refTile = refCols + static_cast<size_t>(refOff) * PW;
-            const float *qryTile = qryCols + static_cast<size_t>(qryOff) * PW;
+            const float4 *refX = reinterpret_cast<const float4 *>(refCols), *refY = refX + 4 * static_cast<long long>(pr.refN4);
+            const float4 *qryX = reinterpret_cast<const float4 *>(qryCols), *qryY = qryX + 4 * static_cast<long long>(pr.qryN4);
             const int prevWarp = (warp + NW - 1) % NW;
             int g0 = 1;
 
@@ -169,8 +168,12 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
                 const float pruneBelow = __fsub_rn(maxScore, xdropF);
 
                 if (tid == 0) {   // warm L1 for the lines the band edges will touch a few diagonals from now
-                    prefetchL1(refTile + static_cast<size_t>(min(refLen - 1, k - L0 + 12)) * PW);
-                    prefetchL1(qryTile + static_cast<size_t>(min(qryLen - 1, Lb + W + 8)) * PW);
+                    // (one 128 B line holds 8 consecutive columns of one stream = a span of 32 columns, so each line is
+                    // touched on four consecutive diagonals; the four streams advance in turn)
+                    const long long jr = ntColIndex(refOff + min(refLen - 1, k - L0 + 40), pr.refN4);
+                    const long long iq = ntColIndex(qryOff + min(qryLen - 1, Lb + W + 40 + (k & 3)), pr.qryN4);
+                    prefetchL1(refX + jr); prefetchL1(refY + jr);
+                    prefetchL1(qryX + iq); prefetchL1(qryY + iq);
                 }
 
                 // row-neighbour of slot 0: last slot of the previous thread (previous warp through shared memory)
@@ -187,9 +190,9 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
                     rowBase = iBase;
 #pragma unroll
                     for (int c = 0; c < kSlots; ++c) {
-                        const int i = min(iBase + c, qryLen - 1);
-                        const float4 x = __ldg(reinterpret_cast<const float4 *>(qryTile + static_cast<size_t>(i) * PW));
-                        const float4 y = __ldg(reinterpret_cast<const float4 *>(qryTile + static_cast<size_t>(i) * PW) + 1);
+                        const long long at = ntColIndex(qryOff + min(iBase + c, qryLen - 1), pr.qryN4);
+                        const float4 x = __ldg(qryX + at);
+                        const float4 y = __ldg(qryY + at);
                         q[c][0] = x.x; q[c][1] = x.y; q[c][2] = x.z; q[c][3] = x.w; q[c][4] = y.x; q[c][5] = y.y;
                         gOpQ[c] = y.z; gExQ[c] = y.w;
                     }
@@ -205,9 +208,9 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
                     bool gapQ = false, gapR = false;
 #pragma unroll
                     for (int c = 0; c < kSlots; ++c) {
-                        const int j = min(max(k - (iBase + c), 0), refLen - 1);
-                        const float4 x = __ldg(reinterpret_cast<const float4 *>(refTile + static_cast<size_t>(j) * PW));
-                        const float4 y = __ldg(reinterpret_cast<const float4 *>(refTile + static_cast<size_t>(j) * PW) + 1);
+                        const long long at = ntColIndex(refOff + min(max(k - (iBase + c), 0), refLen - 1), pr.refN4);
+                        const float4 x = __ldg(refX + at);
+                        const float4 y = __ldg(refY + at);
                         r[c][0] = x.x; r[c][1] = x.y; r[c][2] = x.z; r[c][3] = x.w; r[c][4] = y.x; r[c][5] = y.y;
                         gOpR[c] = y.z; gExR[c] = y.w;
                         gapR = gapR || (y.y != 0.0f);

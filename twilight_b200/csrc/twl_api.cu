@@ -131,8 +131,26 @@ size_t tbBytesPerCta(int marker) {
     return (n + 255) & ~static_cast<size_t>(255);
 }
 
+// words one side of `len` columns occupies in the packed profile buffer
+size_t sideWords(int len, int P) {
+    if (P == 6) return static_cast<size_t>((len + 3) / 4) * 32;   // 8 streams of ceil(len/4) float4
+    return static_cast<size_t>(len) * (P + 2);
+}
+
 void packColumns(float *dst, const float *freq, const float *gapOp, const float *gapEx, int len, int P) {
     const int PW = P + 2;
+    if (P == 6) {   // de-interleaved nucleotide layout, see twl_device.cuh
+        const int n4 = (len + 3) / 4;
+        std::memset(dst, 0, sideWords(len, P) * sizeof(float));
+        for (int c = 0; c < len; ++c) {
+            float *x = dst + twl::ntColIndex(c, n4) * 4;
+            float *y = x + static_cast<size_t>(16) * n4;
+            const float *f = freq + static_cast<size_t>(c) * 6;
+            x[0] = f[0]; x[1] = f[1]; x[2] = f[2]; x[3] = f[3];
+            y[0] = f[4]; y[1] = f[5]; y[2] = gapOp[c]; y[3] = gapEx[c];
+        }
+        return;
+    }
     for (int c = 0; c < len; ++c) {
         float *d = dst + static_cast<size_t>(c) * PW;
         std::memcpy(d, freq + static_cast<size_t>(c) * P, sizeof(float) * P);
@@ -225,7 +243,7 @@ int twl_batch_stage(twl_ctx *ctx, const twl_profile_pair *pairs, int n_pairs) {
     ctx->ran = false;
     ctx->nPairs = n_pairs;
     if (n_pairs == 0) { ctx->staged = true; return TWL_OK; }
-    const int P = ctx->P, PW = P + 2;
+    const int P = ctx->P;
     const int defXdrop = static_cast<int>(1000 * -1 * ctx->gapExtend);     // TALCO-XDrop.cpp:49
     ctx->hPairs.resize(n_pairs);
     size_t words = 0, bytes = 0;
@@ -236,8 +254,9 @@ int twl_batch_stage(twl_ctx *ctx, const twl_profile_pair *pairs, int n_pairs) {
             !in.gap_open_qry || !in.gap_ext_qry)
             return fail(ctx, TWL_E_ARG, "twl_batch_stage: pair " + std::to_string(p) + " has empty profiles or null pointers");
         twl::DevPair &d = ctx->hPairs[p];
-        d.refOff = static_cast<long long>(words); words += static_cast<size_t>(in.ref_len) * PW;
-        d.qryOff = static_cast<long long>(words); words += static_cast<size_t>(in.qry_len) * PW;
+        d.refOff = static_cast<long long>(words); words += sideWords(in.ref_len, P);
+        d.qryOff = static_cast<long long>(words); words += sideWords(in.qry_len, P);
+        d.refN4 = (in.ref_len + 3) / 4; d.qryN4 = (in.qry_len + 3) / 4;
         d.alnOff = static_cast<long long>(bytes); bytes += (static_cast<size_t>(in.ref_len) + in.qry_len + 15) & ~static_cast<size_t>(15);
         d.refLen = in.ref_len; d.qryLen = in.qry_len;
         d.refNum = in.ref_num; d.qryNum = in.qry_num;

@@ -1,10 +1,16 @@
 // twl_device.cuh — device-side types shared by the TALCO-XDrop kernels and the C-ABI host code.
 //
 // HBM layout of a staged level batch (one allocation each, sized by the host per batch):
-//   prof    float  packed column profiles, one column = PW = P+2 floats, 32-byte aligned:
+//   prof    float  packed column profiles, one column = PW = P+2 floats:
 //                  [0..P-1] weighted letter counts (calculateProfile, alignment-helper.cpp:8),
 //                  [P] position-specific gap-open, [P+1] gap-extend (calculatePSGP, alignment-helper.cpp:168).
-//                  PW = 8 for nucleotides (one 32 B sector per column), 24 for proteins.
+//                  Proteins (PW = 24): array of columns, 96 B each.
+//                  Nucleotides (PW = 8): a column is two float4 halves X = (A C G T) and Y = (N gap gapOpen gapExtend),
+//                  and a side of n columns is stored as 8 streams of n4 = ceil(n/4) float4 each:
+//                      X of column j at float4 index (j&3)*n4 + (j>>2),  Y at 4*n4 + (j&3)*n4 + (j>>2).
+//                  The wavefront kernel gives each thread 4 consecutive rows, so at a fixed register slot the 32
+//                  lanes of a warp read columns j, j-4, j-8, ...: with this de-interleaved layout that is ONE
+//                  contiguous 512 B run per LDG.128 (4 L1 wavefronts) instead of 32 different 128 B lines.
 //   pairs   DevPair[nPairs]   where each pair's ref/qry columns start inside `prof`, lengths, counts, per-pair
 //                  Talco parameters (gapCharScore, xdrop, fLen: alignment-cpu.cpp:86-88, 116-129)
 //   paths   int8   alignment paths, pair p at alnOff, capacity refLen+qryLen
@@ -29,7 +35,11 @@ struct DevPair {
     float gapChar;
     int xdrop, fLen;
     int pad;
+    int refN4, qryN4;   // nucleotide layout: stream length ceil(len/4) of each side
 };
+
+// float4 index of the X half of nucleotide column j inside a side with stream length n4 (Y half: + 4*n4)
+__host__ __device__ inline long long ntColIndex(int j, int n4) { return static_cast<long long>(j & 3) * n4 + (j >> 2); }
 
 struct DevResult {
     int status;
