@@ -19,7 +19,12 @@ __device__ __forceinline__ float exactDiv(float num, float den, float rcp) {
     if (an < 1e-18f && an > 0.0f) res = __fdiv_rn(num, den);
     return res;
 }
-
+// The same without the tiny-numerator guard: the caller guarantees num == 0 or |num| >= 2^-60.
+__device__ __forceinline__ float exactDivNormal(float num, float den, float rcp) {
+    const float q = __fmul_rn(num, rcp);
+    const float r = __fmaf_rn(-q, den, num);
+    return __fmaf_rn(r, rcp, q);
+}
 
 // Nucleotide, P = 6. r[0..5], q[0..5] are profile columns, S the 5x5 matrix (row-major, any address space), g the
 // gap-character score.

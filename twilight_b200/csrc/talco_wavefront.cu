@@ -154,6 +154,8 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
             const float4 *qryX = reinterpret_cast<const float4 *>(qryCols), *qryY = qryX + 4 * static_cast<long long>(pr.qryN4);
             const int prevWarp = (warp + NW - 1) % NW;
             int g0 = 1;
+            float2 *const edgeOut = &sh.edge[0][warp];
+            int4 *const redOut = &sh.red[0][warp];
 
             for (int k = 0; k < nDiag; ++k) {
                 g0 ^= 1;
@@ -206,15 +208,27 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
                 if (__any_sync(0xffffffffu, anyAct)) {
                     float r[kSlots][6], gOpR[kSlots], gExR[kSlots], num[kSlots];
                     bool gapQ = false, gapR = false;
+                    {
+                        // Slot c reads global reference column m-c with m = refOff + k - iBase. iBase is a multiple of 4,
+                        // so m&3 is the same for every thread: the four slots hit the four streams of the de-interleaved
+                        // layout at float4 index m>>2 (or one less once m-c crosses a multiple of 4). Columns outside
+                        // [0, refLen) are only touched by slots that are not live; the profile buffer is padded so the
+                        // reads stay inside the allocation and their values are discarded.
+                        const int m = refOff + k - iBase;
+                        const int u = (refOff + k) & 3;
+                        const float4 *pX = refX + (m >> 2);
+                        const long long yOff = 4 * static_cast<long long>(pr.refN4);
 #pragma unroll
-                    for (int c = 0; c < kSlots; ++c) {
-                        const long long at = ntColIndex(refOff + min(max(k - (iBase + c), 0), refLen - 1), pr.refN4);
-                        const float4 x = __ldg(refX + at);
-                        const float4 y = __ldg(refY + at);
-                        r[c][0] = x.x; r[c][1] = x.y; r[c][2] = x.z; r[c][3] = x.w; r[c][4] = y.x; r[c][5] = y.y;
-                        gOpR[c] = y.z; gExR[c] = y.w;
-                        gapR = gapR || (y.y != 0.0f);
-                        gapQ = gapQ || (q[c][5] != 0.0f);
+                        for (int c = 0; c < kSlots; ++c) {
+                            const int stream = (u - c) & 3;
+                            const int at = stream * pr.refN4 - ((c > u) ? 1 : 0);
+                            const float4 x = __ldg(pX + at);
+                            const float4 y = __ldg(pX + at + yOff);
+                            r[c][0] = x.x; r[c][1] = x.y; r[c][2] = x.z; r[c][3] = x.w; r[c][4] = y.x; r[c][5] = y.y;
+                            gOpR[c] = y.z; gExR[c] = y.w;
+                            gapR = gapR || (y.y != 0.0f);
+                            gapQ = gapQ || (q[c][5] != 0.0f);
+                        }
                     }
                     numerators4<MC>(r, q, a, num);
                     // gap-character terms (TALCO-XDrop.cpp:393-394): each loop adds exact zeros unless the query (resp.
@@ -232,8 +246,18 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
                             for (int m = 0; m < 5; ++m) num[c] = __fmaf_rn(__fmul_rn(r[c][5], q[c][m]), gapChar, num[c]);
                     }
                     if (divMode == 1) {
+                        // reciprocal-based exact division; numerators that are non-zero but tiny (|n| < 2^-60, where the
+                        // quotient or the FMA residual could leave the normal range) take the IEEE divide instead
+                        unsigned tiny = 0xffffffffu;
 #pragma unroll
-                        for (int c = 0; c < kSlots; ++c) num[c] = exactDiv(num[c], denom, rcp);
+                        for (int c = 0; c < kSlots; ++c) tiny = min(tiny, (__float_as_uint(num[c]) & 0x7fffffffu) - 1u);
+                        if (tiny < 0x21800000u - 1u) {
+#pragma unroll
+                            for (int c = 0; c < kSlots; ++c) num[c] = __fdiv_rn(num[c], denom);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < kSlots; ++c) num[c] = exactDivNormal(num[c], denom, rcp);
+                        }
                     } else if (divMode == 2) {
 #pragma unroll
                         for (int c = 0; c < kSlots; ++c) num[c] = __fdiv_rn(num[c], denom);
@@ -332,8 +356,8 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
                 const int wMax = __reduce_max_sync(0xffffffffu, orderedInt(myMax));
                 const int wLo = __reduce_min_sync(0xffffffffu, myLo);
                 const int wHi = __reduce_max_sync(0xffffffffu, myHi);
-                if (lane == 31) sh.edge[g0][warp] = make_float2(h1[kSlots - 1], i1[kSlots - 1]);
-                if (lane == 0) sh.red[g0][warp] = make_int4(wMax, wLo, wHi, 0);
+                if (lane == 31) edgeOut[g0 * 8] = make_float2(h1[kSlots - 1], i1[kSlots - 1]);
+                if (lane == 0) redOut[g0 * 8] = make_int4(wMax, wLo, wHi, 0);
                 __syncthreads();
                 int oMax = sh.red[g0][0].x, newL = sh.red[g0][0].y, newU = sh.red[g0][0].z;
 #pragma unroll
@@ -412,6 +436,8 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
                     int state = static_cast<int8_t>(tbState) % 3;
                     const bool first = (tile == 0);
                     while (kk >= 0 && w > 0) {
+                        // the path drifts about half a row per step: pull the line 24 diagonals back into L1 now
+                        if (kk >= 24) prefetchL1(tb + static_cast<size_t>(kk - 24) * W + ((row - 12) & (W - 1)));
                         const int cell = tb[static_cast<size_t>(kk) * W + (row & (W - 1))];
                         int dir;
                         if (state == 0) {

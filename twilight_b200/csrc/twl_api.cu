@@ -122,6 +122,7 @@ int fail(twl_ctx *ctx, int code, const std::string &msg) {
         }                                                                                               \
     } while (0)
 
+constexpr size_t kProfPadWords = 4096;   // 16 KB of slack on both ends of the device profile buffer (wavefront kernel over-reads)
 constexpr int kSmemStateCap = 1020;   // band cells held in shared memory by the narrow generic variant
 constexpr int kNarrowCtasPerSm = 3;
 
@@ -295,14 +296,18 @@ int twl_batch_stage(twl_ctx *ctx, const twl_profile_pair *pairs, int n_pairs) {
         return ctx->hPairs[x].refLen + ctx->hPairs[x].qryLen > ctx->hPairs[y].refLen + ctx->hPairs[y].qryLen;
     });
 
-    TWL_CUDA(ctx, ctx->dProf.reserve(words));
+    {
+        const size_t before = ctx->dProf.cap;
+        TWL_CUDA(ctx, ctx->dProf.reserve(words + 2 * kProfPadWords));
+        if (ctx->dProf.cap != before) TWL_CUDA(ctx, cudaMemsetAsync(ctx->dProf.ptr, 0, ctx->dProf.cap * sizeof(float), ctx->stream));
+    }
     TWL_CUDA(ctx, ctx->dPairs.reserve(n_pairs));
     TWL_CUDA(ctx, ctx->dResults.reserve(n_pairs));
     TWL_CUDA(ctx, ctx->dPaths.reserve(bytes));
     TWL_CUDA(ctx, ctx->dOrder.reserve(n_pairs));
     TWL_CUDA(ctx, ctx->dOverflow.reserve(n_pairs));
     TWL_CUDA(ctx, ctx->dCounters.reserve(8));
-    TWL_CUDA(ctx, cudaMemcpyAsync(ctx->dProf.ptr, ctx->hProf.ptr, words * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    TWL_CUDA(ctx, cudaMemcpyAsync(ctx->dProf.ptr + kProfPadWords, ctx->hProf.ptr, words * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     TWL_CUDA(ctx, cudaMemcpyAsync(ctx->dPairs.ptr, ctx->hPairs.data(), n_pairs * sizeof(twl::DevPair), cudaMemcpyHostToDevice, ctx->stream));
     TWL_CUDA(ctx, cudaMemcpyAsync(ctx->dOrder.ptr, ctx->hOrder.data(), n_pairs * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // hPairs/hOrder are pageable
@@ -362,7 +367,7 @@ int twl_batch_run(twl_ctx *ctx) {
     TWL_CUDA(ctx, cudaEventRecord(ctx->evStart, ctx->stream));
 
     twl::TalcoArgs a{};
-    a.prof = ctx->dProf.ptr;
+    a.prof = ctx->dProf.ptr + kProfPadWords;
     a.pairs = ctx->dPairs.ptr;
     a.results = ctx->dResults.ptr;
     a.paths = ctx->dPaths.ptr;
