@@ -1,0 +1,47 @@
+"""CPU-side checks of the C ABI library: it loads, exports every symbol include/twilight_b200.h declares, and refuses to
+run without a CUDA device (no fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "twilight_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = set(re.findall(r"\b(twl_[a-z_0-9]+)\s*\(", text))
+    assert "twl_align_profiles" in names
+    return sorted(names)
+
+
+def test_library_exports_every_declared_symbol():
+    from twilight_b200 import _lib, build
+    build.build()
+    lib = C.CDLL(_lib.LIB_PATH)
+    for name in declared_symbols():
+        assert hasattr(lib, name), f"{name} declared in twilight_b200.h but not exported"
+    # and the Python binding table covers the header one to one
+    assert sorted(_lib.SIGNATURES) == declared_symbols()
+
+
+def test_no_device_means_hard_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    import twilight_b200
+    with pytest.raises(twilight_b200.TwilightError) as err:
+        twilight_b200.Context()
+    assert "no CPU fallback" in str(err.value) or "NO_DEVICE" in str(err.value)
+
+
+def test_product_package_does_not_touch_the_oracle():
+    """Nothing under twilight_b200/ may import, link or execute oracle/ (it is checker-only infrastructure)."""
+    pkg = os.path.join(ROOT, "twilight_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(base, f), errors="ignore").read()
+                assert "oracle_lib" not in text and "twl_oracle" not in text and "libtalco_ref" not in text, os.path.join(base, f)
