@@ -38,10 +38,13 @@ def test_no_device_means_hard_failure():
 
 
 def test_product_package_does_not_touch_the_oracle():
-    """Nothing under twilight_b200/ may import, link or execute oracle/ (it is checker-only infrastructure)."""
+    """Nothing under twilight_b200/ may import, include, link or execute oracle/ (it is checker-only infrastructure;
+    mentioning it in a comment is fine)."""
     pkg = os.path.join(ROOT, "twilight_b200")
+    bad = re.compile(r'(^\s*(import|from)\s+[\w.]*oracle)|(#\s*include\s*[<"][^>"]*oracle)|(CDLL\([^)]*oracle)|(-l\s*twl_oracle)|(libtalco_ref)|(oracle_lib)', re.M)
     for base, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) or f == "Makefile":
                 text = open(os.path.join(base, f), errors="ignore").read()
-                assert "oracle_lib" not in text and "twl_oracle" not in text and "libtalco_ref" not in text, os.path.join(base, f)
+                hit = bad.search(text)
+                assert hit is None, f"{os.path.join(base, f)}: {hit.group(0)}"
