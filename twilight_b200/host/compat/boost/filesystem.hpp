@@ -1,4 +1,4 @@
-// oracle/compat: boost::filesystem / boost::system mapped onto <filesystem>. TEST INFRASTRUCTURE ONLY.
+// host/compat: boost::filesystem / boost::system mapped onto <filesystem>. TEST INFRASTRUCTURE ONLY.
 #pragma once
 #include <filesystem>
 #include <system_error>

@@ -1,4 +1,4 @@
-// oracle/compat: the slice of boost::program_options that the TWILIGHT CLI uses. TEST INFRASTRUCTURE ONLY —
+// host/compat: the slice of boost::program_options that the TWILIGHT CLI uses. TEST INFRASTRUCTURE ONLY —
 // exists so the unmodified reference host sources compile in an image without Boost headers.
 //
 // Supported: options_description(caption[, width]), add_options()("long,s"[, value<T>()[->default_value(v)]], "help"),

@@ -1,4 +1,4 @@
-// oracle/compat: tbb::global_control stand-in (caps the worker count of compat parallel_for). TEST INFRASTRUCTURE ONLY.
+// host/compat: tbb::global_control stand-in (caps the worker count of compat parallel_for). TEST INFRASTRUCTURE ONLY.
 #pragma once
 #include "parallel_for.h"
 

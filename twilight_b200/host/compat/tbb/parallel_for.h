@@ -1,4 +1,4 @@
-// oracle/compat: minimal stand-in for the oneTBB subset that the TWILIGHT host sources use.
+// host/compat: minimal stand-in for the oneTBB subset that the TWILIGHT host sources use.
 // TEST INFRASTRUCTURE ONLY — lets the *unmodified* reference sources under /root/reference compile in an
 // image that has no TBB. Not part of the product path.
 //

@@ -1,4 +1,4 @@
-// oracle/compat: tbb::spin_rw_mutex stand-in backed by std::shared_mutex. TEST INFRASTRUCTURE ONLY.
+// host/compat: tbb::spin_rw_mutex stand-in backed by std::shared_mutex. TEST INFRASTRUCTURE ONLY.
 #pragma once
 #include <atomic>
 #include <shared_mutex>
