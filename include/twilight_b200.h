@@ -93,6 +93,71 @@ int twl_batch_stage(twl_ctx *ctx, const twl_profile_pair *pairs, int n_pairs);
 int twl_batch_run(twl_ctx *ctx);
 int twl_batch_fetch(twl_ctx *ctx, int8_t *const *paths, twl_pair_result *results);
 
+/* ---- device-resident row store: mirror of SequenceDB::SequenceInfo (src/msa.hpp:113-134, src/sequencedb.cpp:8-76).
+ *      A row is the current (aligned) text of one sequence; the level kernels read and rewrite rows in HBM, ping-pong
+ *      between two buffers per row exactly like alnStorage[2] / changeStorage(). ids are small non-negative integers
+ *      (SequenceInfo::id). ------------------------------------------------------------------------------------- */
+int twl_rows_upload(twl_ctx *ctx, int n, const int32_t *ids, const char *const *rows, const int32_t *lens, const float *weights);
+int twl_rows_download(twl_ctx *ctx, int n, const int32_t *ids, char *const *dst, int32_t *lens);   /* dst[i] holds >= current length */
+int twl_rows_length(twl_ctx *ctx, int32_t id);   /* current length of a row, <0 if unknown */
+int twl_rows_clear(twl_ctx *ctx);
+
+/* ---- one guide-tree level on the resident rows: for every pair calculateProfile + getConsensus +
+ *      removeGappyColumns + calculatePSGP (device), TALCO-XDrop DP + traceback (device), addGappyColumnsBack (host,
+ *      O(path) merge of run lists), updateFrequency + updateAlignment (device). Replaces the body of
+ *      parallelAlignmentCPU (src/alignment-cpu.cpp:46-176) for pairs whose members are all resident rows. ------- */
+typedef struct {
+    const int32_t *seq_ids;     /* member rows in Node::seqsIncluded order */
+    int32_t n_ids;
+    int32_t aln_len;            /* Node::alnLen  */
+    int32_t aln_num;            /* Node::alnNum  */
+    float aln_weight;           /* Node::alnWeight */
+    const float *msa_freq;      /* Node::msaFreq flattened [aln_len][P], or NULL when not cached */
+} twl_node_side;
+
+typedef struct {
+    twl_node_side ref, qry;
+    int32_t flags;              /* TWL_PAIR_PROFILE_ONLY: run calculateProfile (and its msaFreq caching) but no alignment */
+    int32_t reserved;
+} twl_level_pair;
+#define TWL_PAIR_PROFILE_ONLY 1
+
+typedef struct {
+    int32_t status;             /* TWL_ST_*; rows are rewritten only when 0 */
+    int32_t path_len;           /* length of the final path (with gappy columns) = new Node::alnLen */
+    int32_t tiles;
+    int32_t cached;             /* bit 0: ref msaFreq was cached by this call (helper.cpp:35-40), bit 1: qry, bit 2: merged msaFreq available */
+    uint64_t cells;
+    uint64_t diagonals;
+    int32_t ref_len_dp, qry_len_dp;   /* profile lengths after gappy-column removal */
+} twl_level_result;
+
+/* current_task: SequenceDB::currentTask (0 normal, 1 deferred re-alignment, 2 merge): selects gapCharScore and the
+ * error protocol of alignment-cpu.cpp:88,108-129 (tasks 1/2 retry with wider x-drop / fLen inside this call).
+ * gappy_threshold: Option::gappyVertical (0.95; 1.0 disables). cache_threshold: _CAL_PROFILE_TH (1000).
+ * paths[p] (nullable) must hold ref.aln_len + qry.aln_len bytes. */
+int twl_align_level(twl_ctx *ctx, const twl_level_pair *pairs, int n_pairs, int current_task, float gappy_threshold,
+                    int32_t cache_threshold, int8_t *const *paths, twl_level_result *results);
+
+/* Intermediates of the last twl_align_level call, for parity tests and for the caller's msaFreq bookkeeping. */
+#define TWL_F_PROFILE_RAW_REF 0   /* float [aln_len][P] after calculateProfile */
+#define TWL_F_PROFILE_RAW_QRY 1
+#define TWL_F_CONSENSUS_REF 2     /* char [aln_len] */
+#define TWL_F_CONSENSUS_QRY 3
+#define TWL_F_RUNS_REF 4          /* int32 (start,len) pairs of removed gappy-column runs */
+#define TWL_F_RUNS_QRY 5
+#define TWL_F_PATH_WO 6           /* int8 path before addGappyColumnsBack */
+#define TWL_F_FREQ_REF 7          /* float [aln_len][P] msaFreq cached for the ref node by this call */
+#define TWL_F_FREQ_QRY 8
+#define TWL_F_FREQ_MERGED 9       /* float [path_len][P] merged msaFreq (updateFrequency) */
+#define TWL_F_DP_PROFILE_REF 10   /* float [ref_len_dp][P+2]: compacted columns + gapOpen + gapExtend (row-major view of the packed layout) */
+#define TWL_F_DP_PROFILE_QRY 11
+int twl_level_fetch(twl_ctx *ctx, int pair, int what, void *dst, size_t cap_bytes, size_t *out_bytes);
+
+/* Device time of the last twl_align_level call by phase, milliseconds: [0] profile build, [1] gappy/PSGP/pack,
+ * [2] DP chain, [3] row update + frequency merge. */
+int twl_level_phase_ms(twl_ctx *ctx, float out[4]);
+
 /* Device time (CUDA events on the context's stream) of the kernels of the last run(), in milliseconds, and the number
  * of kernel launches it issued. */
 float twl_last_kernel_ms(const twl_ctx *ctx);

@@ -1,0 +1,92 @@
+"""GPU parity of the level pipeline (twl_rows_* + twl_align_level) against the CPU oracle, stage by stage:
+calculateProfile / getConsensus / removeGappyColumns / calculatePSGP / DP / addGappyColumnsBack / updateFrequency /
+updateAlignment. Every comparison is bit-exact."""
+import numpy as np
+import pytest
+
+from tests import oracle_lib as ol, ref_msa
+from twilight_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def run_tree_on_gpu(ctx, tree, seqs, weights, cfg, gappy, cache_threshold, check_stages=True):
+    """Drives align_level bottom-up and compares each pair with the oracle's record of the same pair."""
+    import twilight_b200
+    from twilight_b200 import api
+    ctx.rows_clear()
+    ctx.rows_upload(list(range(tree.n_leaves)), seqs, weights)
+    gpu = {i: dict(ids=[i], aln_len=len(seqs[i]), aln_num=1, aln_weight=float(np.float32(weights[i])), freq=None) for i in range(tree.n_leaves)}
+    cpu = {i: ref_msa.leaf_state(seqs[i], weights[i]) for i in range(tree.n_leaves)}
+    cpu_ids = {i: [i] for i in range(tree.n_leaves)}
+    n_pairs = 0
+    for level in synth.levels_bottom_up(tree):
+        pairs, recs = [], []
+        for a, b, parent in level:
+            ga, gb = gpu[a], gpu[b]
+            pairs.append(twilight_b200.LevelPairIn(
+                twilight_b200.NodeSideIn(ga["ids"], ga["aln_len"], ga["aln_num"], ga["aln_weight"], ga["freq"]),
+                twilight_b200.NodeSideIn(gb["ids"], gb["aln_len"], gb["aln_num"], gb["aln_weight"], gb["freq"])))
+            recs.append(ref_msa.align_pair("n", cfg, cpu.pop(a), cpu.pop(b), gappy, 0, None, cache_threshold))
+        outs = ctx.align_level(pairs, task=0, gappy=gappy, cache_threshold=cache_threshold)
+        for k, ((a, b, parent), o, r) in enumerate(zip(level, outs, recs)):
+            tag = f"pair ({a},{b})"
+            assert o.status == r.error == 0, tag
+            if check_stages:
+                for s in (0, 1):
+                    assert np.array_equal(ctx.level_fetch(k, api.F_PROFILE_RAW[s]), r.profile_raw[s]), f"{tag} raw profile side {s}"
+                    assert ctx.level_fetch(k, api.F_CONSENSUS[s]).tobytes() == r.consensus[s], f"{tag} consensus side {s}"
+                    assert np.array_equal(ctx.level_fetch(k, api.F_RUNS[s]), np.asarray(r.runs[s], np.int32).reshape(-1, 2)), f"{tag} gappy runs side {s}"
+                    dp = ctx.level_fetch(k, api.F_DP_PROFILE[s])
+                    assert np.array_equal(dp[:, :cfg.P], r.profile[s]), f"{tag} compacted profile side {s}"
+                    assert np.array_equal(dp[:, cfg.P], r.gap_op[s]) and np.array_equal(dp[:, cfg.P + 1], r.gap_ex[s]), f"{tag} PSGP side {s}"
+                assert np.array_equal(ctx.level_fetch(k, api.F_PATH_WO), r.aln_wo), f"{tag} DP path"
+            assert o.cells == r.cells and o.tiles == r.tiles, tag
+            assert np.array_equal(o.path, r.aln_w), f"{tag} final path"
+            ids = gpu[a]["ids"] + gpu[b]["ids"]
+            freq = None
+            if o.merged_freq:
+                freq = ctx.level_fetch(k, api.F_FREQ_MERGED)
+                assert r.merged.msa_freq is not None and np.array_equal(freq, r.merged.msa_freq), f"{tag} merged msaFreq"
+            else:
+                assert r.merged.msa_freq is None, tag
+            gpu[parent] = dict(ids=ids, aln_len=len(o.path), aln_num=gpu[a]["aln_num"] + gpu[b]["aln_num"],
+                               aln_weight=float(np.float32(gpu[a]["aln_weight"]) + np.float32(gpu[b]["aln_weight"])), freq=freq)
+            cpu[parent] = r.merged
+            rows = ctx.rows_download(ids)
+            assert rows == r.merged.rows, f"{tag} rewritten rows"
+            n_pairs += 1
+    return n_pairs
+
+
+@pytest.mark.parametrize("n,L,seed,marker,gappy,cache", [
+    (8, 300, 0, 1024, 0.95, 1000),
+    (24, 600, 1, 256, 0.6, 1000),     # low threshold: gappy-column runs on both sides, consensus re-alignment
+    (16, 900, 2, 128, 0.95, 4),       # tiny cache threshold: msaFreq caching, cached-profile branch, frequency merge
+    (12, 1500, 3, 1024, 1.0, 1000),   # gappy removal disabled
+])
+def test_level_pipeline_matches_oracle(n, L, seed, marker, gappy, cache):
+    import twilight_b200
+    tree = synth.random_tree(n, seed=seed, mean_blen=0.06)
+    seqs = synth.evolve(tree, L, seed=seed, indel_rate=0.08)
+    w = np.random.default_rng(seed + 1).uniform(0.5, 1.5, n).astype(np.float32)
+    cfg = ol.TalcoCfg(marker=marker)
+    ctx = twilight_b200.Context(marker=marker)
+    done = run_tree_on_gpu(ctx, tree, seqs, w, cfg, gappy, cache)
+    ctx.close()
+    assert done == n - 1
+
+
+def test_rows_roundtrip_and_errors():
+    import twilight_b200
+    ctx = twilight_b200.Context()
+    rows = [b"ACGT-ACGTNN", b"A", b"", b"acgu" * 1000]
+    ctx.rows_upload([3, 0, 7, 2], rows, [1.0, 2.0, 0.5, 1.5])
+    assert ctx.rows_download([2, 7, 0, 3]) == [rows[3], rows[2], rows[1], rows[0]]
+    with pytest.raises(twilight_b200.TwilightError):
+        ctx.rows_download([5])
+    side = twilight_b200.NodeSideIn([3], 999, 1, 1.0)   # wrong length
+    with pytest.raises(twilight_b200.TwilightError):
+        ctx.align_level([twilight_b200.LevelPairIn(side, twilight_b200.NodeSideIn([0], 1, 1, 2.0))])
+    assert ctx.align_level([]) == []
+    ctx.close()

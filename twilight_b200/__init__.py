@@ -4,4 +4,5 @@ The product is the CUDA library `libtwilight_b200.so` (C ABI in include/twilight
 sources (csrc/), the build recipe, the ctypes binding and the host-side mirror of the reference's level-kernel
 interface. There is no CPU implementation in this package.
 """
-from .api import Context, PairOut, ProfilePairIn, TwilightError, nucleotide_matrix  # noqa: F401
+from .api import (Context, LevelOut, LevelPairIn, NodeSideIn, PairOut, ProfilePairIn, TwilightError,  # noqa: F401
+                  nucleotide_matrix)

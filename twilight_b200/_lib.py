@@ -24,6 +24,23 @@ class PairResult(C.Structure):
                 ("cells", C.c_uint64), ("diagonals", C.c_uint64)]
 
 
+class NodeSide(C.Structure):
+    """twl_node_side"""
+    _fields_ = [("seq_ids", C.POINTER(C.c_int32)), ("n_ids", C.c_int32), ("aln_len", C.c_int32), ("aln_num", C.c_int32),
+                ("aln_weight", C.c_float), ("msa_freq", C.c_void_p)]
+
+
+class LevelPair(C.Structure):
+    """twl_level_pair"""
+    _fields_ = [("ref", NodeSide), ("qry", NodeSide), ("flags", C.c_int32), ("reserved", C.c_int32)]
+
+
+class LevelResult(C.Structure):
+    """twl_level_result"""
+    _fields_ = [("status", C.c_int32), ("path_len", C.c_int32), ("tiles", C.c_int32), ("cached", C.c_int32),
+                ("cells", C.c_uint64), ("diagonals", C.c_uint64), ("ref_len_dp", C.c_int32), ("qry_len_dp", C.c_int32)]
+
+
 # name -> (restype, argtypes); mirrors include/twilight_b200.h one to one (tests check the export list against it)
 SIGNATURES = {
     "twl_device_count": (C.c_int, []),
@@ -36,6 +53,13 @@ SIGNATURES = {
     "twl_batch_stage": (C.c_int, [C.c_void_p, C.POINTER(ProfilePair), C.c_int]),
     "twl_batch_run": (C.c_int, [C.c_void_p]),
     "twl_batch_fetch": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(PairResult)]),
+    "twl_rows_upload": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_char_p), C.POINTER(C.c_int32), C.POINTER(C.c_float)]),
+    "twl_rows_download": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
+    "twl_rows_length": (C.c_int, [C.c_void_p, C.c_int32]),
+    "twl_rows_clear": (C.c_int, [C.c_void_p]),
+    "twl_align_level": (C.c_int, [C.c_void_p, C.POINTER(LevelPair), C.c_int, C.c_int, C.c_float, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(LevelResult)]),
+    "twl_level_fetch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "twl_level_phase_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "twl_last_kernel_ms": (C.c_float, [C.c_void_p]),
     "twl_last_launch_count": (C.c_int, [C.c_void_p]),
     "twl_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),

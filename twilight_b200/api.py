@@ -42,6 +42,45 @@ class PairOut:
     diagonals: int
 
 
+@dataclass
+class NodeSideIn:
+    """One node of a pair for align_level: member row ids in seqsIncluded order + Node::alnLen/alnNum/alnWeight/msaFreq."""
+    seq_ids: Sequence[int]
+    aln_len: int
+    aln_num: int
+    aln_weight: float
+    msa_freq: Optional[np.ndarray] = None
+
+
+@dataclass
+class LevelPairIn:
+    ref: NodeSideIn
+    qry: NodeSideIn
+    profile_only: bool = False
+
+
+@dataclass
+class LevelOut:
+    status: int
+    path: np.ndarray            # final path (with gappy columns); its length is the merged node's alnLen
+    tiles: int
+    cells: int
+    cached_ref: bool
+    cached_qry: bool
+    merged_freq: bool
+    ref_len_dp: int
+    qry_len_dp: int
+
+
+F_PROFILE_RAW = (0, 1)
+F_CONSENSUS = (2, 3)
+F_RUNS = (4, 5)
+F_PATH_WO = 6
+F_FREQ = (7, 8)
+F_FREQ_MERGED = 9
+F_DP_PROFILE = (10, 11)
+
+
 def nucleotide_matrix(match=18.0, mismatch=-8.0, transition=-4.0, wildcard=False) -> np.ndarray:
     """msa::Params nucleotide scoring matrix (src/scoring-matrix.cpp:103-112): A C G T/U N."""
     m = np.zeros((5, 5), np.float32)
@@ -142,6 +181,76 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self._lib.twl_last_launch_count(self._h))
+
+    # ---- device-resident rows + level pipeline -----------------------------------------------------------------------
+    def rows_upload(self, ids: Sequence[int], rows: Sequence[bytes], weights: Sequence[float]):
+        n = len(ids)
+        a_ids = (C.c_int32 * n)(*[int(i) for i in ids])
+        a_rows = (C.c_char_p * n)(*rows)
+        a_lens = (C.c_int32 * n)(*[len(r) for r in rows])
+        a_w = (C.c_float * n)(*[float(w) for w in weights])
+        self._check(self._lib.twl_rows_upload(self._h, n, a_ids, a_rows, a_lens, a_w))
+
+    def rows_download(self, ids: Sequence[int]) -> List[bytes]:
+        n = len(ids)
+        a_ids = (C.c_int32 * n)(*[int(i) for i in ids])
+        lens = [self._lib.twl_rows_length(self._h, int(i)) for i in ids]
+        bufs = [C.create_string_buffer(max(l, 1)) for l in lens]
+        ptrs = (C.c_void_p * n)(*[C.addressof(b) for b in bufs])
+        out_l = (C.c_int32 * n)()
+        self._check(self._lib.twl_rows_download(self._h, n, a_ids, ptrs, out_l))
+        return [bufs[k].raw[:out_l[k]] for k in range(n)]
+
+    def rows_clear(self):
+        self._check(self._lib.twl_rows_clear(self._h))
+
+    def align_level(self, pairs: Sequence[LevelPairIn], task: int = 0, gappy: float = 0.95, cache_threshold: int = 1000) -> List[LevelOut]:
+        n = len(pairs)
+        arr = (_lib.LevelPair * max(n, 1))()
+        keep = []
+        caps = []
+        for k, p in enumerate(pairs):
+            for side, dst in ((p.ref, arr[k].ref), (p.qry, arr[k].qry)):
+                ids = (C.c_int32 * max(len(side.seq_ids), 1))(*[int(i) for i in side.seq_ids])
+                keep.append(ids)
+                dst.seq_ids = ids
+                dst.n_ids = len(side.seq_ids)
+                dst.aln_len, dst.aln_num, dst.aln_weight = int(side.aln_len), int(side.aln_num), float(side.aln_weight)
+                if side.msa_freq is not None:
+                    f = np.ascontiguousarray(side.msa_freq, np.float32)
+                    keep.append(f)
+                    dst.msa_freq = f.ctypes.data
+                else:
+                    dst.msa_freq = None
+            arr[k].flags = 1 if p.profile_only else 0
+            caps.append(p.ref.aln_len + p.qry.aln_len)
+        bufs = [np.zeros(max(c, 1), np.int8) for c in caps]
+        ptrs = (C.c_void_p * max(n, 1))(*[b.ctypes.data for b in bufs])
+        res = (_lib.LevelResult * max(n, 1))()
+        self._check(self._lib.twl_align_level(self._h, arr, n, int(task), float(gappy), int(cache_threshold), ptrs, res))
+        return [LevelOut(res[k].status, bufs[k][:res[k].path_len].copy(), res[k].tiles, int(res[k].cells), bool(res[k].cached & 1),
+                         bool(res[k].cached & 2), bool(res[k].cached & 4), res[k].ref_len_dp, res[k].qry_len_dp) for k in range(n)]
+
+    def level_fetch(self, pair: int, what: int) -> np.ndarray:
+        size = C.c_size_t(0)
+        self._check(self._lib.twl_level_fetch(self._h, pair, what, None, 0, C.byref(size)))
+        raw = np.zeros(max(size.value, 1), np.uint8)
+        self._check(self._lib.twl_level_fetch(self._h, pair, what, raw.ctypes.data, raw.size, C.byref(size)))
+        raw = raw[:size.value]
+        if what in F_CONSENSUS:
+            return raw
+        if what in F_RUNS:
+            return raw.view(np.int32).reshape(-1, 2)
+        if what == F_PATH_WO:
+            return raw.view(np.int8)
+        out = raw.view(np.float32)
+        width = self.P + 2 if what in F_DP_PROFILE else self.P
+        return out.reshape(-1, width)
+
+    def level_phase_ms(self):
+        out = (C.c_float * 4)()
+        self._check(self._lib.twl_level_phase_ms(self._h, out))
+        return [float(x) for x in out]
 
     # ---- one-call interface (host buffers in, host buffers out) -------------------------------------------------
     def align_profiles(self, pairs: Sequence[ProfilePairIn]) -> List[PairOut]:

@@ -1,0 +1,324 @@
+// level_kernels.cuh — the HBM-bound kernels around the DP of one guide-tree level:
+//   profileBuildKernel   calculateProfile + getConsensus + msaFreq cache   (src/alignment-helper.cpp:8-72, 221-241)
+//   gappyCompactKernel   removeGappyColumns + calculatePSGP, fused, writing the DP kernels' packed layout directly
+//                        (src/alignment-helper.cpp:74-166, 168-219)
+//   pathChunkKernel      per-1024-op prefix counts of a final alignment path
+//   rowUpdateKernel      alignment_helper::updateAlignment row rewrite + updateFrequency merge
+//                        (src/alignment-helper.cpp:377-448, 506-539)
+// All arithmetic that reaches a float result follows the reference's operation order and types.
+#pragma once
+#include "twl_device.cuh"
+
+namespace twl {
+
+constexpr int kLvlThreads = 256;
+constexpr int kPathChunk = 1024;
+
+// One side (node) of a pair as the level kernels see it.
+struct DevSide {
+    long long memberOff;    // first entry of this side in the member arrays (row pointers, weights)
+    long long rawOff;       // floats: raw profile [alnLen][P] (calculateProfile output)
+    long long consOff;      // bytes : consensus [alnLen]
+    long long freqInOff;    // floats: cached msaFreq uploaded by the caller, or -1
+    long long freqOutOff;   // floats: where the msaFreq cache is written when storeFreq, or -1
+    long long profOff;      // floats: packed DP-layout columns of this side inside the DP `prof` buffer
+    long long runsOff;      // ints  : (start,len) pairs of removed column runs
+    int nRows, alnLen, alnNum;
+    float nodeWeight;
+    int pairIdx, isQry;     // which DevPair field this side fills
+    int newLen, nRuns;      // outputs of gappyCompactKernel
+};
+
+struct DevUpdate {          // one pair of rowUpdateKernel
+    long long pathOff;      // bytes: final path (with gappy columns) of this pair
+    long long chunkOff;     // ints : per-chunk prefix counts (2 per chunk: ref-consuming, qry-consuming)
+    long long memberOff;    // first member (ref members, then qry members) in rowIn/rowOut
+    long long freqRefOff, freqQryOff, mergedOff;   // floats, -1 when the frequency merge does not apply
+    int pathLen, nRef, nQry;
+    float refWeight, qryWeight;
+    int pad;
+};
+
+__device__ __forceinline__ int letterIndexNt(unsigned char c) {   // letterIdx after toupper, scoring-matrix.cpp:55-79
+    if (c >= 'a' && c <= 'z') c -= 32;
+    switch (c) {
+    case 'A': return 0;
+    case 'C': return 1;
+    case 'G': return 2;
+    case 'T': case 'U': return 3;
+    case '-': case '.': return 5;
+    default: return 4;
+    }
+}
+
+__device__ __forceinline__ int letterIndexAa(unsigned char c, const signed char *lut) { return lut[c]; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// calculateProfile: thread = one column; member rows are visited in seqsIncluded order so the float accumulation
+// order equals the reference's. Accumulators live in shared memory ([letter][thread], conflict free) because the
+// letter index is data dependent.
+// ---------------------------------------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(kLvlThreads) profileBuildKernel(const DevSide *sides, const char *const *rowPtr, const float *rowWeight,
+                                                                  float *raw, char *cons, const float *freqIn, float *freqOut,
+                                                                  const signed char *aaLut) {
+    __shared__ float acc[P][kLvlThreads];
+    // grid.x = side (the dimension with the 2^31 limit), grid.y = block of kLvlThreads columns
+    const DevSide sd = sides[blockIdx.x];
+    const int t = blockIdx.y * kLvlThreads + threadIdx.x;
+    if (blockIdx.y * kLvlThreads >= sd.alnLen) return;
+    const bool live = t < sd.alnLen;
+    float col[P];
+    if (sd.freqInOff >= 0) {                                               // helper.cpp:16-21
+        if (live) {
+#pragma unroll
+            for (int v = 0; v < P; ++v) col[v] = __fmul_rn(__fdiv_rn(freqIn[sd.freqInOff + static_cast<long long>(t) * P + v], sd.nodeWeight), static_cast<float>(sd.alnNum));
+        }
+    } else {                                                               // helper.cpp:23-34
+#pragma unroll
+        for (int v = 0; v < P; ++v) acc[v][threadIdx.x] = 0.0f;
+        const char *const *rows = rowPtr + sd.memberOff;
+        const float *wts = rowWeight + sd.memberOff;
+        for (int s = 0; s < sd.nRows; ++s) {
+            const float w = __fmul_rn(__fdiv_rn(wts[s], sd.nodeWeight), static_cast<float>(sd.alnNum));
+            if (live) {
+                const unsigned char ch = static_cast<unsigned char>(rows[s][t]);
+                const int letter = (P == 6) ? letterIndexNt(ch) : letterIndexAa(ch, aaLut);
+                acc[letter][threadIdx.x] = __fadd_rn(acc[letter][threadIdx.x], w);
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < P; ++v) col[v] = acc[v][threadIdx.x];
+    }
+    if (!live) return;
+    float *dst = raw + sd.rawOff + static_cast<long long>(t) * P;
+#pragma unroll
+    for (int v = 0; v < P; ++v) dst[v] = col[v];
+    if (sd.freqOutOff >= 0) {                                              // helper.cpp:35-40
+        float *f = freqOut + sd.freqOutOff + static_cast<long long>(t) * P;
+#pragma unroll
+        for (int v = 0; v < P; ++v) f[v] = __fmul_rn(__fdiv_rn(col[v], static_cast<float>(sd.alnNum)), sd.nodeWeight);
+    }
+    // getConsensus, helper.cpp:221-241: strict > from 0 over the first P-2 letters, default = the ambiguity letter
+    int best = P - 2;
+    float top = 0.0f;
+#pragma unroll
+    for (int v = 0; v < P - 2; ++v)
+        if (col[v] > top) { top = col[v]; best = v; }
+    const char *lut = (P == 6) ? "ACGTN" : "ACDEFGHIKLMNPQRSTVWYX";
+    cons[sd.consOff + t] = lut[best];
+}
+
+// block-wide exclusive scan of one int per thread (kLvlThreads threads); returns the exclusive prefix, total in *total
+__device__ __forceinline__ int blockExclusiveScan(int v, int *warpSums, int *total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += n;
+    }
+    if (lane == 31) warpSums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = (lane < kLvlThreads / 32) ? warpSums[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += n;
+        }
+        if (lane < kLvlThreads / 32) warpSums[lane] = w;
+    }
+    __syncthreads();
+    const int base = warp ? warpSums[warp - 1] : 0;
+    *total = warpSums[kLvlThreads / 32 - 1];
+    __syncthreads();
+    return base + inc - v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// removeGappyColumns + calculatePSGP + packing. One CTA per side. Pass A counts the kept columns (the packed nucleotide
+// layout needs the final length up front), pass B scans, writes the kept columns with their position-specific gap
+// penalties in the DP layout and emits the (start,len) list of removed runs for addGappyColumnsBack.
+// ---------------------------------------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(kLvlThreads) gappyCompactKernel(DevSide *sides, const float *raw, float *prof, int *runs, DevPair *pairs,
+                                                                  float threshold, float gapOpen, float gapExtend) {
+    __shared__ int warpSums[kLvlThreads / 32];
+    __shared__ int sTotal;
+    DevSide &sdRef = sides[blockIdx.x];
+    const DevSide sd = sdRef;
+    const float *col = raw + sd.rawOff;
+    const bool enabled = (threshold != 1.0f);                               // helper.cpp:77
+    const float numF = static_cast<float>(sd.alnNum);
+
+    int kept = 0;
+    for (int t = threadIdx.x; t < sd.alnLen; t += kLvlThreads) {
+        const bool gappy = enabled && (__fdiv_rn(col[static_cast<long long>(t) * P + P - 1], numF) > threshold);   // helper.cpp:84
+        kept += gappy ? 0 : 1;
+    }
+    int total;
+    blockExclusiveScan(kept, warpSums, &total);
+    const int newLen = total;
+    const int n4 = (newLen + 3) / 4;
+    float *out = prof + sd.profOff;
+
+    const float scale = (P == 6) ? 0.5f : 1.0f;                             // helper.cpp:179
+    const float minExtend = static_cast<float>(static_cast<double>(gapExtend) * 0.2);   // helper.cpp:180-181
+    const float minOpen = static_cast<float>(static_cast<double>(gapOpen) * 0.1);
+    const float openScaled = __fmul_rn(gapOpen, scale);
+
+    int keptBase = 0, runBase = 0;
+    for (int c0 = 0; c0 < sd.alnLen; c0 += kLvlThreads) {
+        const int t = c0 + threadIdx.x;
+        const bool live = t < sd.alnLen;
+        bool gappy = false, prevGappy = false, nextGappy = false;
+        float v[P];
+        if (live) {
+#pragma unroll
+            for (int x = 0; x < P; ++x) v[x] = col[static_cast<long long>(t) * P + x];
+            if (enabled) {
+                gappy = __fdiv_rn(v[P - 1], numF) > threshold;
+                prevGappy = (t > 0) && (__fdiv_rn(col[static_cast<long long>(t - 1) * P + P - 1], numF) > threshold);
+                nextGappy = (t + 1 < sd.alnLen) && (__fdiv_rn(col[static_cast<long long>(t + 1) * P + P - 1], numF) > threshold);
+            }
+        }
+        const int isKept = (live && !gappy) ? 1 : 0;
+        const int isStart = (live && gappy && !prevGappy) ? 1 : 0;
+        int chunkKept, chunkStarts;
+        const int idx = keptBase + blockExclusiveScan(isKept, warpSums, &chunkKept);
+        const int runIdxIncl = runBase + blockExclusiveScan(isStart, warpSums, &chunkStarts) + isStart;
+        if (isKept) {
+            // calculatePSGP, helper.cpp:185-196 (the ratio is evaluated in double, as upstream)
+            const float g = v[P - 1];
+            float gOp = gapOpen, gEx = gapExtend;
+            if (g > 0) {
+                const double keep = static_cast<double>(__fsub_rn(numF, g)) * 1.0 / static_cast<double>(sd.alnNum);
+                gOp = fminf(minOpen, static_cast<float>(static_cast<double>(openScaled) * keep));
+                gEx = fminf(minExtend, static_cast<float>(static_cast<double>(gapExtend) * keep));
+            }
+            if (P == 6) {
+                float4 *x = reinterpret_cast<float4 *>(out) + ntColIndex(idx, n4);
+                float4 *y = x + 4 * static_cast<long long>(n4);
+                *x = make_float4(v[0], v[1], v[2], v[3]);
+                *y = make_float4(v[4], v[5], gOp, gEx);
+            } else {
+                float *d = out + static_cast<long long>(idx) * (P + 2);
+#pragma unroll
+                for (int x = 0; x < P; ++x) d[x] = v[x];
+                d[P] = gOp; d[P + 1] = gEx;
+            }
+        }
+        if (live && gappy) {
+            int *r = runs + sd.runsOff;
+            if (isStart) r[2 * (runIdxIncl - 1)] = t;
+            if (!nextGappy) r[2 * (runIdxIncl - 1) + 1] = t;   // run end; turned into a length below
+        }
+        keptBase += chunkKept;
+        runBase += chunkStarts;
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < runBase; g += kLvlThreads) {
+        int *r = runs + sd.runsOff + 2 * g;
+        r[1] = r[1] - r[0] + 1;
+    }
+    if (threadIdx.x == 0) {
+        sdRef.newLen = newLen;
+        sdRef.nRuns = runBase;
+        DevPair &pr = pairs[sd.pairIdx];
+        if (sd.isQry) { pr.qryLen = newLen; pr.qryN4 = n4; }
+        else { pr.refLen = newLen; pr.refN4 = n4; }
+    }
+    (void)sTotal;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Per-chunk prefix counts of a final path: chunk c gets (#ref-consuming ops, #qry-consuming ops) in path[0, c*1024).
+// One warp per pair.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void pathChunkKernel(const DevUpdate *ups, int nPairs, const int8_t *paths, int *chunkCounts) {
+    const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (pair >= nPairs) return;
+    const DevUpdate u = ups[pair];
+    const int8_t *path = paths + u.pathOff;
+    int *out = chunkCounts + u.chunkOff;
+    int accR = 0, accQ = 0;
+    const int nChunks = (u.pathLen + kPathChunk - 1) / kPathChunk;
+    for (int c = 0; c < nChunks; ++c) {
+        if (lane == 0) { out[2 * c] = accR; out[2 * c + 1] = accQ; }
+        int r = 0, q = 0;
+        const int end = min(u.pathLen, (c + 1) * kPathChunk);
+        for (int k = c * kPathChunk + lane; k < end; k += 32) {
+            const int op = path[k];
+            r += (op == 0 || op == 2);
+            q += (op == 0 || op == 1);
+        }
+        accR += __reduce_add_sync(0xffffffffu, r);
+        accQ += __reduce_add_sync(0xffffffffu, q);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// updateAlignment (helper.cpp:381-401, 428-448) and updateFrequency (helper.cpp:506-539). grid = (pair, chunk).
+// The block scans its 1024 path ops once and reuses the source indices for every member row of the pair.
+// ---------------------------------------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(kLvlThreads) rowUpdateKernel(const DevUpdate *ups, const int8_t *paths, const int *chunkCounts,
+                                                               const char *const *rowIn, char *const *rowOut, const float *freq, float *merged) {
+    __shared__ int warpSums[kLvlThreads / 32];
+    __shared__ int srcR[kPathChunk], srcQ[kPathChunk];
+    __shared__ int8_t ops[kPathChunk];
+    const DevUpdate u = ups[blockIdx.x];          // grid.x = pair, grid.y = chunk of kPathChunk path ops
+    const int k0 = blockIdx.y * kPathChunk;
+    if (k0 >= u.pathLen) return;
+    const int8_t *path = paths + u.pathOff;
+    const int baseR = chunkCounts[u.chunkOff + 2 * blockIdx.y], baseQ = chunkCounts[u.chunkOff + 2 * blockIdx.y + 1];
+    constexpr int PER = kPathChunk / kLvlThreads;   // 4 consecutive ops per thread
+    int r[PER], q[PER], sumR = 0, sumQ = 0;
+#pragma unroll
+    for (int e = 0; e < PER; ++e) {
+        const int k = k0 + threadIdx.x * PER + e;
+        const int op = (k < u.pathLen) ? path[k] : 3;
+        ops[threadIdx.x * PER + e] = static_cast<int8_t>(op);
+        r[e] = (op == 0 || op == 2); q[e] = (op == 0 || op == 1);
+        sumR += r[e]; sumQ += q[e];
+    }
+    int tot;
+    int exR = baseR + blockExclusiveScan(sumR, warpSums, &tot);
+    int exQ = baseQ + blockExclusiveScan(sumQ, warpSums, &tot);
+#pragma unroll
+    for (int e = 0; e < PER; ++e) {
+        srcR[threadIdx.x * PER + e] = exR; exR += r[e];
+        srcQ[threadIdx.x * PER + e] = exQ; exQ += q[e];
+    }
+    __syncthreads();
+    const int nHere = min(kPathChunk, u.pathLen - k0);
+    // member rows: ref members copy on 0/2, qry members on 0/1, '-' otherwise
+    for (int m = 0; m < u.nRef + u.nQry; ++m) {
+        const bool isRef = m < u.nRef;
+        const char *in = rowIn[u.memberOff + m];
+        char *out = rowOut[u.memberOff + m] + k0;
+        for (int e = threadIdx.x; e < nHere; e += kLvlThreads) {
+            const int op = ops[e];
+            const bool take = (op == 0) || (op == (isRef ? 2 : 1));
+            out[e] = take ? in[isRef ? srcR[e] : srcQ[e]] : '-';
+        }
+    }
+    if (u.mergedOff >= 0) {                                                 // updateFrequency, helper.cpp:513-531
+        const float *fr = freq + u.freqRefOff, *fq = freq + u.freqQryOff;
+        float *mg = merged + u.mergedOff + static_cast<long long>(k0) * P;
+        for (int x = threadIdx.x; x < nHere * P; x += kLvlThreads) {
+            const int e = x / P, v = x - e * P;
+            const int op = ops[e];
+            float val;
+            if (op == 0) val = __fadd_rn(fr[static_cast<long long>(srcR[e]) * P + v], fq[static_cast<long long>(srcQ[e]) * P + v]);
+            else if (op == 1) { val = fq[static_cast<long long>(srcQ[e]) * P + v]; if (v == P - 1) val = __fadd_rn(val, u.refWeight); }
+            else if (op == 2) { val = fr[static_cast<long long>(srcR[e]) * P + v]; if (v == P - 1) val = __fadd_rn(val, u.qryWeight); }
+            else val = 0.0f;
+            mg[x] = val;
+        }
+    }
+}
+
+} // namespace twl

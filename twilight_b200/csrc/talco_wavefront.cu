@@ -106,6 +106,14 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
         if (work >= *a.nWorkPtr) break;
         const int pairIdx = a.order[work];
         const DevPair pr = a.pairs[pairIdx];
+        if (pr.refLen < 1 || pr.qryLen < 1) {   // an empty side (after gappy-column removal): nothing to align, the host emits the trivial path
+            if (tid == 0) {
+                DevResult res;
+                res.status = kStatusEmptySide; res.pathLen = 0; res.tiles = 0; res.pad = 0; res.cells = 0; res.diagonals = 0;
+                a.results[pairIdx] = res;
+            }
+            continue;
+        }
         const float *refCols = a.prof + pr.refOff;
         const float *qryCols = a.prof + pr.qryOff;
         int8_t *path = a.paths + pr.alnOff;

@@ -1,8 +1,7 @@
 // twl_api.cu — host side of the C ABI declared in include/twilight_b200.h: context lifecycle, batch staging in
 // pinned memory, kernel launches on one stream, result download. No CPU alignment code lives here: if CUDA is not
 // usable every entry point fails.
-#include "../../include/twilight_b200.h"
-#include "twl_device.cuh"
+#include "twl_ctx.hpp"
 
 #include <algorithm>
 #include <cstdio>
@@ -28,101 +27,8 @@ namespace {
 
 std::string g_initError;
 
-template <typename T>
-struct DevBuf {
-    T *ptr = nullptr;
-    size_t cap = 0; // elements
-    cudaError_t reserve(size_t n) {
-        if (n <= cap) return cudaSuccess;
-        if (ptr) cudaFree(ptr);
-        ptr = nullptr;
-        cap = 0;
-        size_t want = n + n / 4 + 256;
-        cudaError_t e = cudaMalloc(&ptr, want * sizeof(T));
-        if (e != cudaSuccess) { e = cudaMalloc(&ptr, n * sizeof(T)); want = n; }
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
-};
+int fail(twl_ctx *ctx, int code, const std::string &msg) { return twlFail(ctx, code, msg); }
 
-template <typename T>
-struct PinBuf {
-    T *ptr = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t n) {
-        if (n <= cap) return cudaSuccess;
-        if (ptr) cudaFreeHost(ptr);
-        ptr = nullptr;
-        cap = 0;
-        size_t want = n + n / 4 + 256;
-        cudaError_t e = cudaMallocHost(&ptr, want * sizeof(T));
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release() { if (ptr) cudaFreeHost(ptr); ptr = nullptr; cap = 0; }
-};
-
-} // namespace
-
-struct twl_ctx {
-    int device = 0;
-    int smCount = 0;
-    cudaStream_t stream = nullptr;
-    bool ownStream = true;
-    cudaEvent_t evStart = nullptr, evStop = nullptr;
-    std::string error;
-
-    // scoring
-    int M = 0, P = 0;
-    float gapOpen = 0, gapExtend = 0, gapBoundary = 0;
-    int marker = twl::kMaxMarker;
-    DevBuf<float> dScore;
-    std::vector<float> hScore;
-
-    // staged batch
-    int nPairs = 0;
-    bool staged = false, ran = false;
-    size_t profWords = 0, pathBytes = 0;
-    std::vector<twl::DevPair> hPairs;
-    std::vector<int> hOrder;
-    int maxFLen = 0;
-    PinBuf<float> hProf;
-    PinBuf<int8_t> hPaths;
-    PinBuf<twl::DevResult> hResults;
-    DevBuf<float> dProf;
-    DevBuf<twl::DevPair> dPairs;
-    DevBuf<twl::DevResult> dResults;
-    DevBuf<int8_t> dPaths;
-    DevBuf<int> dOrder, dOverflow;
-    DevBuf<int> dCounters; // [0] queue A, [1] nWork A, [2] queue B, [3] overflow count (= nWork B)
-    DevBuf<uint8_t> dTb;
-    DevBuf<float> dState;
-
-    bool forceGeneric = false;   // route nucleotide batches through the generic kernel (A/B parity + benchmarking)
-    float lastMs = -1.0f;
-    int lastLaunches = 0;
-    bool timingPending = false;
-};
-
-namespace {
-
-int fail(twl_ctx *ctx, int code, const std::string &msg) {
-    if (ctx) ctx->error = msg;
-    else g_initError = msg;
-    return code;
-}
-
-#define TWL_CUDA(ctx, call)                                                                             \
-    do {                                                                                                \
-        cudaError_t e_ = (call);                                                                        \
-        if (e_ != cudaSuccess) {                                                                        \
-            return fail(ctx, (e_ == cudaErrorMemoryAllocation) ? TWL_E_NOMEM : TWL_E_CUDA,              \
-                        std::string(#call) + ": " + cudaGetErrorString(e_));                            \
-        }                                                                                               \
-    } while (0)
-
-constexpr size_t kProfPadWords = 4096;   // 16 KB of slack on both ends of the device profile buffer (wavefront kernel over-reads)
 constexpr int kSmemStateCap = 1020;   // band cells held in shared memory by the narrow generic variant
 constexpr int kNarrowCtasPerSm = 3;
 
@@ -161,6 +67,12 @@ void packColumns(float *dst, const float *freq, const float *gapOp, const float 
 }
 
 } // namespace
+
+int twlFail(twl_ctx *ctx, int code, const std::string &msg) {
+    if (ctx) ctx->error = msg;
+    else g_initError = msg;
+    return code;
+}
 
 extern "C" {
 
@@ -206,6 +118,7 @@ void twl_destroy(twl_ctx *ctx) {
     if (ctx->evStart) cudaEventDestroy(ctx->evStart);
     if (ctx->evStop) cudaEventDestroy(ctx->evStop);
     if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    twlLevelDestroy(ctx);
     delete ctx;
 }
 
@@ -315,23 +228,16 @@ int twl_batch_stage(twl_ctx *ctx, const twl_profile_pair *pairs, int n_pairs) {
     return TWL_OK;
 }
 
-int twl_batch_run(twl_ctx *ctx) {
-    if (!ctx) return TWL_E_ARG;
-    if (!ctx->staged) return fail(ctx, TWL_E_STATE, "twl_batch_run: no staged batch");
-    cudaSetDevice(ctx->device);
-    ctx->lastLaunches = 0;
-    ctx->lastMs = 0.0f;
-    ctx->timingPending = false;
-    if (ctx->nPairs == 0) { ctx->ran = true; return TWL_OK; }
-    const int n = ctx->nPairs;
-    const int marker = ctx->marker;
-    const int wideCap = std::max(ctx->maxFLen, 8);                 // widest band any pair of the batch may legally reach
-    const bool nucleotide = (ctx->P == 6) && !ctx->forceGeneric;
+} // extern "C"
 
-    // Kernel chain. Every stage reads its work list + count from device memory and appends the pairs whose band
-    // outgrew its capacity to the next stage's list, so the whole chain is enqueued without a host round trip.
-    //   nucleotide: wavefront<128> (band <= 512) -> wavefront<256> (band <= 1024) -> generic/global state (any band)
-    //   protein   : generic/shared state (band <= 1020)                            -> generic/global state
+// Kernel chain. Every stage reads its work list + count from device memory and appends the pairs whose band outgrew its
+// capacity to the next stage's list, so the whole chain is enqueued without a host round trip.
+//   nucleotide: wavefront<128> (band <= 509) -> wavefront<256> (band <= 1021) -> generic/global state (any band)
+//   protein   : generic/shared state (band <= 1020)                            -> generic/global state
+int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
+    const int marker = ctx->marker;
+    const int wideCap = std::max(wideCapIn, 8);                     // widest band any pair of the batch may legally reach
+    const bool nucleotide = (ctx->P == 6) && !ctx->forceGeneric;
     struct Stage { int kind; int threads; int cap; int grid; size_t tbStride; };   // kind 0 wavefront, 1 generic smem, 2 generic global
     const int matClass = nucleotide ? twl::nucleotideMatrixClass(ctx->hScore.data()) : 0;
     std::vector<Stage> stages;
@@ -364,7 +270,6 @@ int twl_batch_run(twl_ctx *ctx) {
     counters[1] = n;
     TWL_CUDA(ctx, ctx->dCounters.reserve(16));
     TWL_CUDA(ctx, cudaMemcpyAsync(ctx->dCounters.ptr, counters, sizeof(counters), cudaMemcpyHostToDevice, ctx->stream));
-    TWL_CUDA(ctx, cudaEventRecord(ctx->evStart, ctx->stream));
 
     twl::TalcoArgs a{};
     a.prof = ctx->dProf.ptr + kProfPadWords;
@@ -393,6 +298,22 @@ int twl_batch_run(twl_ctx *ctx) {
         else TWL_CUDA(ctx, twl::launchTalcoGeneric(ctx->P, st.kind == 2, a, st.grid, st.kind == 1 ? twl::genericStateWords(st.cap) * sizeof(float) : 0, ctx->stream));
         ctx->lastLaunches += 1;
     }
+    return TWL_OK;
+}
+
+extern "C" {
+
+int twl_batch_run(twl_ctx *ctx) {
+    if (!ctx) return TWL_E_ARG;
+    if (!ctx->staged) return fail(ctx, TWL_E_STATE, "twl_batch_run: no staged batch");
+    cudaSetDevice(ctx->device);
+    ctx->lastLaunches = 0;
+    ctx->lastMs = 0.0f;
+    ctx->timingPending = false;
+    if (ctx->nPairs == 0) { ctx->ran = true; return TWL_OK; }
+    TWL_CUDA(ctx, cudaEventRecord(ctx->evStart, ctx->stream));
+    const int rc = twlLaunchDpChain(ctx, ctx->nPairs, ctx->maxFLen);
+    if (rc != TWL_OK) return rc;
     TWL_CUDA(ctx, cudaEventRecord(ctx->evStop, ctx->stream));
     ctx->timingPending = true;
     ctx->ran = true;

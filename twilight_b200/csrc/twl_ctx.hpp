@@ -1,0 +1,103 @@
+// twl_ctx.hpp — host-side context shared by the C-ABI translation units (twl_api.cu: batch DP; twl_level.cu: the
+// device-resident level pipeline).
+#pragma once
+#include "../../include/twilight_b200.h"
+#include "twl_device.cuh"
+
+#include <string>
+#include <vector>
+
+template <typename T>
+struct DevBuf {
+    T *ptr = nullptr;
+    size_t cap = 0; // elements
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        size_t want = n + n / 4 + 256;
+        cudaError_t e = cudaMalloc(&ptr, want * sizeof(T));
+        if (e != cudaSuccess) { e = cudaMalloc(&ptr, n * sizeof(T)); want = n; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
+};
+
+template <typename T>
+struct PinBuf {
+    T *ptr = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (ptr) cudaFreeHost(ptr);
+        ptr = nullptr;
+        cap = 0;
+        size_t want = n + n / 4 + 256;
+        cudaError_t e = cudaMallocHost(&ptr, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (ptr) cudaFreeHost(ptr); ptr = nullptr; cap = 0; }
+};
+
+struct TwlLevelState;   // twl_level.cu
+
+struct twl_ctx {
+    int device = 0;
+    int smCount = 0;
+    cudaStream_t stream = nullptr;
+    bool ownStream = true;
+    cudaEvent_t evStart = nullptr, evStop = nullptr;
+    std::string error;
+
+    // scoring
+    int M = 0, P = 0;
+    float gapOpen = 0, gapExtend = 0, gapBoundary = 0;
+    int marker = twl::kMaxMarker;
+    DevBuf<float> dScore;
+    std::vector<float> hScore;
+
+    // staged batch
+    int nPairs = 0;
+    bool staged = false, ran = false;
+    size_t profWords = 0, pathBytes = 0;
+    std::vector<twl::DevPair> hPairs;
+    std::vector<int> hOrder;
+    int maxFLen = 0;
+    PinBuf<float> hProf;
+    PinBuf<int8_t> hPaths;
+    PinBuf<twl::DevResult> hResults;
+    DevBuf<float> dProf;
+    DevBuf<twl::DevPair> dPairs;
+    DevBuf<twl::DevResult> dResults;
+    DevBuf<int8_t> dPaths;
+    DevBuf<int> dOrder, dOverflow;
+    DevBuf<int> dCounters; // per chain stage: [2s] queue cursor, [2s+1] work count
+    DevBuf<uint8_t> dTb;
+    DevBuf<float> dState;
+
+    bool forceGeneric = false;   // route nucleotide batches through the generic kernel (A/B parity + benchmarking)
+    float lastMs = -1.0f;
+    int lastLaunches = 0;
+    bool timingPending = false;
+
+    TwlLevelState *level = nullptr;
+};
+
+constexpr size_t kProfPadWords = 4096;   // 16 KB of slack on both ends of the device profile buffer (wavefront kernel over-reads)
+
+int twlFail(twl_ctx *ctx, int code, const std::string &msg);
+// Enqueues the DP kernel chain over ctx->dPairs / dProf / dOrder (n pairs, widest legal band wideCap); no timing events.
+int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCap);
+void twlLevelDestroy(twl_ctx *ctx);
+
+#define TWL_CUDA(ctx, call)                                                                             \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            return twlFail(ctx, (e_ == cudaErrorMemoryAllocation) ? TWL_E_NOMEM : TWL_E_CUDA,           \
+                           std::string(#call) + ": " + cudaGetErrorString(e_));                         \
+        }                                                                                               \
+    } while (0)

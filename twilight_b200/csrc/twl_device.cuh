@@ -24,6 +24,7 @@ namespace twl {
 constexpr int kMaxMarker = 1024;          // Talco_xdrop::Params::marker, TALCO-XDrop.cpp:51
 constexpr int kInsBoundary = -2;          // I_BOUNDARY, TALCO-XDrop.cpp:33
 constexpr int kDelBoundary = -3;          // D_BOUNDARY, TALCO-XDrop.cpp:34
+constexpr int kStatusEmptySide = 200;     // internal: one side has no columns
 constexpr int kStatusRetryWide = 100;     // internal: band exceeded this kernel's state capacity, rerun on the wide variant
 
 struct DevPair {

@@ -1,0 +1,684 @@
+// twl_level.cu — device-resident row store and the per-level pipeline (twl_rows_*, twl_align_level, twl_level_fetch).
+// Host orchestration only; the kernels are in level_kernels.cuh and talco_*.cu.
+#include "level_kernels.cuh"
+#include "twl_ctx.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+namespace {
+
+struct RowSlot {
+    char *buf[2] = {nullptr, nullptr};
+    int cap = 0, len = 0, storage = 0;
+    float weight = 0.f;
+    bool present = false;
+};
+
+struct PairKeep {   // what twl_level_fetch needs from the last level
+    long long rawOff[2] = {-1, -1}, consOff[2] = {-1, -1}, runsOff[2] = {-1, -1}, profOff[2] = {-1, -1};
+    int alnLen[2] = {0, 0}, newLen[2] = {0, 0}, nRuns[2] = {0, 0};
+    long long pathWoOff = -1;
+    int pathWoLen = 0;
+    std::vector<float> freq[2], merged;
+    std::vector<int32_t> runs[2];
+    std::vector<char> cons[2];
+    std::vector<int8_t> pathWo;
+    int chunk = 0;
+};
+
+} // namespace
+
+struct TwlLevelState {
+    std::vector<RowSlot> rows;
+    std::vector<void *> pools;
+    char *poolCur = nullptr;
+    size_t poolLeft = 0;
+
+    DevBuf<twl::DevSide> dSides;
+    DevBuf<const char *> dRowIn;
+    DevBuf<char *> dRowOut;
+    DevBuf<float> dRowW, dRaw, dFreq, dMerged;
+    DevBuf<char> dCons;
+    DevBuf<int> dRuns, dChunkCounts;
+    DevBuf<twl::DevUpdate> dUps;
+    DevBuf<int8_t> dFinalPaths;
+    DevBuf<signed char> dAaLut;
+    bool lutReady = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float phaseMs[4] = {0, 0, 0, 0};
+
+    std::vector<PairKeep> keep;
+    int lastChunks = 0;
+    int P = 0;
+};
+
+namespace {
+
+constexpr size_t kPoolChunkBytes = static_cast<size_t>(256) << 20;
+
+TwlLevelState *levelOf(twl_ctx *ctx) {
+    if (!ctx->level) {
+        ctx->level = new TwlLevelState();
+        for (auto &e : ctx->level->ev) cudaEventCreate(&e);
+    }
+    return ctx->level;
+}
+
+cudaError_t poolAlloc(TwlLevelState *L, size_t bytes, char **out) {
+    bytes = (bytes + 15) & ~static_cast<size_t>(15);
+    if (bytes > L->poolLeft) {
+        const size_t sz = std::max(kPoolChunkBytes, bytes);
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, sz);
+        if (e != cudaSuccess) return e;
+        L->pools.push_back(p);
+        L->poolCur = static_cast<char *>(p);
+        L->poolLeft = sz;
+    }
+    *out = L->poolCur;
+    L->poolCur += bytes;
+    L->poolLeft -= bytes;
+    return cudaSuccess;
+}
+
+// ---- addGappyColumnsBack + pairwiseGlobal (src/alignment-helper.cpp:324-375, 243-322): O(path) serial merge of the
+// removed-run lists back into the DP path; runs removed on both sides at the same point are aligned against each other by
+// a small affine-gap global alignment of the two consensus substrings with free end gaps. Host code: the data is a few
+// KB per pair and strictly sequential.
+int letterIndexHost(char type, char c) {
+    if (c >= 'a' && c <= 'z') c = static_cast<char>(c - 32);
+    if (type == 'p') {
+        static const char *aa = "ACDEFGHIKLMNPQRSTVWY";
+        if (c == '-' || c == '.') return 21;
+        const char *hit = c ? std::strchr(aa, c) : nullptr;
+        return hit ? static_cast<int>(hit - aa) : 20;
+    }
+    switch (c) {
+    case 'A': return 0;
+    case 'C': return 1;
+    case 'G': return 2;
+    case 'T': case 'U': return 3;
+    case '-': case '.': return 5;
+    default: return 4;
+    }
+}
+
+void consensusGlobal(char type, const std::vector<float> &score, int M, float gapOpen, float gapExtend, const char *s1, int m,
+                     const char *s2, int n, std::vector<int8_t> &out) {
+    const size_t W = static_cast<size_t>(n) + 1;
+    std::vector<float> Mm((m + 1) * W, 0.0f), X((m + 1) * W, 0.0f), Y((m + 1) * W, 0.0f);
+    std::vector<int8_t> tb((m + 1) * W, 0);
+    for (int i = 1; i <= m; ++i) { Y[i * W] = -1e9; tb[i * W] = 2; }
+    for (int j = 1; j <= n; ++j) { X[j] = -1e9; tb[j] = 1; }
+    for (int i = 1; i <= m; ++i)
+        for (int j = 1; j <= n; ++j) {
+            const float base = score[letterIndexHost(type, s1[i - 1]) * M + letterIndexHost(type, s2[j - 1])];
+            const size_t c = i * W + j, up = (i - 1) * W + j, left = i * W + j - 1, dg = (i - 1) * W + j - 1;
+            Mm[c] = base + std::max({Mm[dg], X[dg], Y[dg]});
+            X[c] = std::max(Mm[up] + gapOpen, X[up] + gapExtend);
+            Y[c] = std::max(Mm[left] + gapOpen, Y[left] + gapExtend);
+            const float best = std::max({Mm[c], X[c], Y[c]});
+            tb[c] = (best == Mm[c]) ? 0 : ((best == Y[c]) ? 1 : 2);
+        }
+    std::vector<int8_t> rev;
+    int i = m, j = n;
+    while (i > 0 || j > 0) {
+        const int8_t d = tb[i * W + j];
+        rev.push_back(d);
+        if (d == 0) { --i; --j; } else if (d == 1) { --j; } else { --i; }
+    }
+    out.insert(out.end(), rev.rbegin(), rev.rend());
+}
+
+void restoreGappyColumns(char type, const std::vector<float> &score, int M, float gapOpen, float gapExtend, const int8_t *aln, int alnLen,
+                         const int32_t *runsR, int nR, const int32_t *runsQ, int nQ, const char *consR, const char *consQ,
+                         std::vector<int8_t> &out) {
+    int r = 0, q = 0, gr = 0, gq = 0;
+    for (int a = 0; a <= alnLen; ++a) {
+        const bool hitR = gr < nR && r == runsR[2 * gr];
+        const bool hitQ = gq < nQ && q == runsQ[2 * gq];
+        if (hitR && hitQ) {
+            const int lr = runsR[2 * gr + 1], lq = runsQ[2 * gq + 1];
+            consensusGlobal(type, score, M, gapOpen, gapExtend, consR + r, lr, consQ + q, lq, out);
+            ++gr; ++gq; r += lr; q += lq;
+        } else {
+            if (hitR) { out.insert(out.end(), runsR[2 * gr + 1], 2); r += runsR[2 * gr + 1]; ++gr; }
+            if (hitQ) { out.insert(out.end(), runsQ[2 * gq + 1], 1); q += runsQ[2 * gq + 1]; ++gq; }
+        }
+        if (a < alnLen) {
+            out.push_back(aln[a]);
+            if (aln[a] == 0) { ++r; ++q; } else if (aln[a] == 1) { ++q; } else if (aln[a] == 2) { ++r; }
+        }
+    }
+}
+
+size_t sideWordsL(int len, int P) { return (P == 6) ? static_cast<size_t>((len + 3) / 4) * 32 : static_cast<size_t>(len) * (P + 2); }
+
+} // namespace
+
+void twlLevelDestroy(twl_ctx *ctx) {
+    TwlLevelState *L = ctx->level;
+    if (!L) return;
+    for (void *p : L->pools) cudaFree(p);
+    L->dSides.release(); L->dRowIn.release(); L->dRowOut.release(); L->dRowW.release(); L->dRaw.release(); L->dFreq.release();
+    L->dMerged.release(); L->dCons.release(); L->dRuns.release(); L->dChunkCounts.release(); L->dUps.release();
+    L->dFinalPaths.release(); L->dAaLut.release();
+    for (auto &e : L->ev) if (e) cudaEventDestroy(e);
+    delete L;
+    ctx->level = nullptr;
+}
+
+extern "C" {
+
+int twl_rows_clear(twl_ctx *ctx) {
+    if (!ctx) return TWL_E_ARG;
+    TwlLevelState *L = levelOf(ctx);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (void *p : L->pools) cudaFree(p);
+    L->pools.clear();
+    L->poolCur = nullptr;
+    L->poolLeft = 0;
+    L->rows.clear();
+    return TWL_OK;
+}
+
+int twl_rows_upload(twl_ctx *ctx, int n, const int32_t *ids, const char *const *rows, const int32_t *lens, const float *weights) {
+    if (!ctx) return TWL_E_ARG;
+    if (n < 0 || (n > 0 && (!ids || !rows || !lens || !weights))) return twlFail(ctx, TWL_E_ARG, "twl_rows_upload: null argument");
+    TwlLevelState *L = levelOf(ctx);
+    cudaSetDevice(ctx->device);
+    size_t total = 0;
+    for (int i = 0; i < n; ++i) {
+        if (ids[i] < 0 || lens[i] < 0) return twlFail(ctx, TWL_E_ARG, "twl_rows_upload: negative id or length");
+        total += (static_cast<size_t>(lens[i]) + 15) & ~static_cast<size_t>(15);
+    }
+    PinBuf<char> stage;
+    TWL_CUDA(ctx, stage.reserve(std::max<size_t>(total, 16)));
+    size_t at = 0;
+    for (int i = 0; i < n; ++i) {
+        const int id = ids[i];
+        if (static_cast<size_t>(id) >= L->rows.size()) L->rows.resize(id + 1);
+        RowSlot &r = L->rows[id];
+        const int cap = std::max(16, 2 * lens[i]);                        // timesBigger = 2, sequencedb.cpp:40
+        if (!r.present || r.cap < lens[i]) {
+            TWL_CUDA(ctx, poolAlloc(L, cap, &r.buf[0]));
+            TWL_CUDA(ctx, poolAlloc(L, cap, &r.buf[1]));
+            r.cap = cap;
+        }
+        r.len = lens[i]; r.storage = 0; r.weight = weights[i]; r.present = true;
+        std::memcpy(stage.ptr + at, rows[i], lens[i]);
+        TWL_CUDA(ctx, cudaMemcpyAsync(r.buf[0], stage.ptr + at, lens[i], cudaMemcpyHostToDevice, ctx->stream));
+        at += (static_cast<size_t>(lens[i]) + 15) & ~static_cast<size_t>(15);
+    }
+    TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    stage.release();
+    return TWL_OK;
+}
+
+int twl_rows_length(twl_ctx *ctx, int32_t id) {
+    if (!ctx || !ctx->level || id < 0 || static_cast<size_t>(id) >= ctx->level->rows.size() || !ctx->level->rows[id].present) return -1;
+    return ctx->level->rows[id].len;
+}
+
+int twl_rows_download(twl_ctx *ctx, int n, const int32_t *ids, char *const *dst, int32_t *lens) {
+    if (!ctx) return TWL_E_ARG;
+    if (n < 0 || (n > 0 && (!ids || !dst))) return twlFail(ctx, TWL_E_ARG, "twl_rows_download: null argument");
+    TwlLevelState *L = levelOf(ctx);
+    cudaSetDevice(ctx->device);
+    size_t total = 0;
+    for (int i = 0; i < n; ++i) {
+        if (ids[i] < 0 || static_cast<size_t>(ids[i]) >= L->rows.size() || !L->rows[ids[i]].present)
+            return twlFail(ctx, TWL_E_ARG, "twl_rows_download: unknown row id " + std::to_string(ids[i]));
+        total += (static_cast<size_t>(L->rows[ids[i]].len) + 15) & ~static_cast<size_t>(15);
+    }
+    PinBuf<char> stage;
+    TWL_CUDA(ctx, stage.reserve(std::max<size_t>(total, 16)));
+    size_t at = 0;
+    for (int i = 0; i < n; ++i) {
+        const RowSlot &r = L->rows[ids[i]];
+        TWL_CUDA(ctx, cudaMemcpyAsync(stage.ptr + at, r.buf[r.storage], r.len, cudaMemcpyDeviceToHost, ctx->stream));
+        at += (static_cast<size_t>(r.len) + 15) & ~static_cast<size_t>(15);
+    }
+    TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    at = 0;
+    for (int i = 0; i < n; ++i) {
+        const RowSlot &r = L->rows[ids[i]];
+        std::memcpy(dst[i], stage.ptr + at, r.len);
+        if (lens) lens[i] = r.len;
+        at += (static_cast<size_t>(r.len) + 15) & ~static_cast<size_t>(15);
+    }
+    stage.release();
+    return TWL_OK;
+}
+
+int twl_level_phase_ms(twl_ctx *ctx, float out[4]) {
+    if (!ctx || !out) return TWL_E_ARG;
+    for (int i = 0; i < 4; ++i) out[i] = ctx->level ? ctx->level->phaseMs[i] : 0.f;
+    return TWL_OK;
+}
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// twl_align_level
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct ChunkPlan { int begin, end; };
+
+template <int P>
+int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, int begin, int end, int task, float threshold,
+                  int cacheTh, int8_t *const *paths, twl_level_result *results, int chunkNo) {
+    using namespace twl;
+    const int n = end - begin;
+    const int nSides = 2 * n;
+    const char type = (P == 6) ? 'n' : 'p';
+    const int defXdrop = static_cast<int>(1000 * -1 * ctx->gapExtend);
+    std::vector<DevSide> sides(nSides);
+    std::vector<const char *> rowIn;
+    std::vector<float> rowW;
+    std::vector<DevPair> dp(n);
+    std::vector<float> freqStage;
+    size_t rawWords = 0, consBytes = 0, runInts = 0, profWords = 0, pathBytes = 0, freqWords = 0;
+    int maxLen = 0, maxF = 0;
+
+    for (int p = 0; p < n; ++p) {
+        const twl_level_pair &in = pairs[begin + p];
+        PairKeep &kp = L->keep[begin + p];
+        kp = PairKeep();
+        kp.chunk = chunkNo;
+        const twl_node_side *sd[2] = {&in.ref, &in.qry};
+        const bool store = (in.ref.aln_num >= cacheTh || in.qry.aln_num >= cacheTh) || (in.ref.msa_freq || in.qry.msa_freq);   // helper.cpp:14
+        for (int s = 0; s < 2; ++s) {
+            const twl_node_side &nd = *sd[s];
+            if (nd.aln_len < 0 || nd.aln_num < 1 || nd.n_ids < 0 || (nd.n_ids > 0 && !nd.seq_ids))
+                return twlFail(ctx, TWL_E_ARG, "twl_align_level: malformed node in pair " + std::to_string(begin + p));
+            if (!nd.msa_freq && nd.n_ids == 0)
+                return twlFail(ctx, TWL_E_ARG, "twl_align_level: node without rows and without msa_freq in pair " + std::to_string(begin + p));
+            DevSide &d = sides[2 * p + s];
+            d.memberOff = static_cast<long long>(rowIn.size());
+            for (int m = 0; m < nd.n_ids; ++m) {
+                const int id = nd.seq_ids[m];
+                if (id < 0 || static_cast<size_t>(id) >= L->rows.size() || !L->rows[id].present)
+                    return twlFail(ctx, TWL_E_ARG, "twl_align_level: row " + std::to_string(id) + " is not resident");
+                const RowSlot &r = L->rows[id];
+                if (r.len != nd.aln_len) return twlFail(ctx, TWL_E_ARG, "twl_align_level: row " + std::to_string(id) + " has length " + std::to_string(r.len) + ", node says " + std::to_string(nd.aln_len));
+                rowIn.push_back(r.buf[r.storage]);
+                rowW.push_back(r.weight);
+            }
+            d.rawOff = static_cast<long long>(rawWords); rawWords += static_cast<size_t>(nd.aln_len) * P;
+            d.consOff = static_cast<long long>(consBytes); consBytes += (static_cast<size_t>(nd.aln_len) + 15) & ~static_cast<size_t>(15);
+            d.runsOff = static_cast<long long>(runInts); runInts += 2 * (static_cast<size_t>(nd.aln_len) / 2 + 2);
+            d.profOff = static_cast<long long>(profWords); profWords += sideWordsL(nd.aln_len, P);
+            d.freqInOff = -1; d.freqOutOff = -1;
+            if (nd.msa_freq) {
+                d.freqInOff = static_cast<long long>(freqWords);
+                freqStage.insert(freqStage.end(), nd.msa_freq, nd.msa_freq + static_cast<size_t>(nd.aln_len) * P);
+                freqWords += static_cast<size_t>(nd.aln_len) * P;
+            } else if (store) {
+                d.freqOutOff = static_cast<long long>(freqWords);
+                freqStage.resize(freqStage.size() + static_cast<size_t>(nd.aln_len) * P, 0.f);
+                freqWords += static_cast<size_t>(nd.aln_len) * P;
+            }
+            d.nRows = nd.msa_freq ? 0 : nd.n_ids;
+            d.alnLen = nd.aln_len; d.alnNum = nd.aln_num; d.nodeWeight = nd.aln_weight;
+            d.pairIdx = p; d.isQry = s; d.newLen = 0; d.nRuns = 0;
+            kp.rawOff[s] = d.rawOff; kp.consOff[s] = d.consOff; kp.runsOff[s] = d.runsOff; kp.profOff[s] = d.profOff; kp.alnLen[s] = nd.aln_len;
+            maxLen = std::max(maxLen, nd.aln_len);
+        }
+        DevPair &q = dp[p];
+        q.refOff = sides[2 * p].profOff; q.qryOff = sides[2 * p + 1].profOff;
+        q.alnOff = static_cast<long long>(pathBytes); pathBytes += (static_cast<size_t>(in.ref.aln_len) + in.qry.aln_len + 15) & ~static_cast<size_t>(15);
+        q.refLen = 0; q.qryLen = 0; q.refN4 = 0; q.qryN4 = 0;
+        q.refNum = static_cast<float>(in.ref.aln_num); q.qryNum = static_cast<float>(in.qry.aln_num);
+        q.gapChar = (task == 1 || task == 2 || in.ref.aln_num > 10000 || in.qry.aln_num > 10000) ? 0.0f : ctx->gapExtend;   // alignment-cpu.cpp:88
+        q.xdrop = defXdrop; q.fLen = 4096; q.pad = 0;
+        kp.pathWoOff = q.alnOff;
+        maxF = std::max(maxF, std::min(q.fLen, std::min(in.ref.aln_len, in.qry.aln_len)));
+    }
+
+    // ---- upload the level description
+    TWL_CUDA(ctx, L->dSides.reserve(nSides));
+    TWL_CUDA(ctx, L->dRowIn.reserve(std::max<size_t>(rowIn.size(), 1)));
+    TWL_CUDA(ctx, L->dRowW.reserve(std::max<size_t>(rowW.size(), 1)));
+    TWL_CUDA(ctx, L->dRaw.reserve(std::max<size_t>(rawWords, 1)));
+    TWL_CUDA(ctx, L->dCons.reserve(std::max<size_t>(consBytes, 16)));
+    TWL_CUDA(ctx, L->dRuns.reserve(std::max<size_t>(runInts, 2)));
+    TWL_CUDA(ctx, L->dFreq.reserve(std::max<size_t>(freqWords, 1)));
+    {
+        const size_t before = ctx->dProf.cap;
+        TWL_CUDA(ctx, ctx->dProf.reserve(profWords + 2 * kProfPadWords));
+        if (ctx->dProf.cap != before) TWL_CUDA(ctx, cudaMemsetAsync(ctx->dProf.ptr, 0, ctx->dProf.cap * sizeof(float), ctx->stream));
+    }
+    TWL_CUDA(ctx, ctx->dPairs.reserve(n));
+    TWL_CUDA(ctx, ctx->dResults.reserve(n));
+    TWL_CUDA(ctx, ctx->dPaths.reserve(std::max<size_t>(pathBytes, 16)));
+    TWL_CUDA(ctx, ctx->dOrder.reserve(n));
+    std::vector<int> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+        return pairs[begin + x].ref.aln_len + pairs[begin + x].qry.aln_len > pairs[begin + y].ref.aln_len + pairs[begin + y].qry.aln_len;
+    });
+    if (P == 22 && !L->lutReady) {
+        signed char lut[256];
+        for (int c = 0; c < 256; ++c) lut[c] = static_cast<signed char>(letterIndexHost('p', static_cast<char>(c)));
+        TWL_CUDA(ctx, L->dAaLut.reserve(256));
+        TWL_CUDA(ctx, cudaMemcpyAsync(L->dAaLut.ptr, lut, 256, cudaMemcpyHostToDevice, ctx->stream));
+        TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        L->lutReady = true;
+    }
+    TWL_CUDA(ctx, cudaMemcpyAsync(L->dSides.ptr, sides.data(), sizeof(DevSide) * nSides, cudaMemcpyHostToDevice, ctx->stream));
+    if (!rowIn.empty()) {
+        TWL_CUDA(ctx, cudaMemcpyAsync(L->dRowIn.ptr, rowIn.data(), sizeof(char *) * rowIn.size(), cudaMemcpyHostToDevice, ctx->stream));
+        TWL_CUDA(ctx, cudaMemcpyAsync(L->dRowW.ptr, rowW.data(), sizeof(float) * rowW.size(), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (freqWords) TWL_CUDA(ctx, cudaMemcpyAsync(L->dFreq.ptr, freqStage.data(), sizeof(float) * freqWords, cudaMemcpyHostToDevice, ctx->stream));
+    TWL_CUDA(ctx, cudaMemcpyAsync(ctx->dPairs.ptr, dp.data(), sizeof(DevPair) * n, cudaMemcpyHostToDevice, ctx->stream));
+    TWL_CUDA(ctx, cudaMemcpyAsync(ctx->dOrder.ptr, order.data(), sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
+
+    // ---- phase 1: profiles + consensus (+ msaFreq cache); phase 2: gappy-column compaction + PSGP + DP packing
+    TWL_CUDA(ctx, cudaEventRecord(L->ev[0], ctx->stream));
+    {
+        dim3 grid(nSides, std::max(1, (maxLen + kLvlThreads - 1) / kLvlThreads));
+        profileBuildKernel<P><<<grid, kLvlThreads, 0, ctx->stream>>>(L->dSides.ptr, L->dRowIn.ptr, L->dRowW.ptr, L->dRaw.ptr, L->dCons.ptr,
+                                                                 L->dFreq.ptr, L->dFreq.ptr, L->dAaLut.ptr);
+        TWL_CUDA(ctx, cudaGetLastError());
+    }
+    TWL_CUDA(ctx, cudaEventRecord(L->ev[1], ctx->stream));
+    gappyCompactKernel<P><<<nSides, kLvlThreads, 0, ctx->stream>>>(L->dSides.ptr, L->dRaw.ptr, ctx->dProf.ptr + kProfPadWords, L->dRuns.ptr,
+                                                                   ctx->dPairs.ptr, threshold, ctx->gapOpen, ctx->gapExtend);
+    TWL_CUDA(ctx, cudaGetLastError());
+    TWL_CUDA(ctx, cudaEventRecord(L->ev[2], ctx->stream));
+    ctx->lastLaunches += 2;
+
+    // ---- phase 3: DP chain (pairs flagged profile-only are parked with an impossible work order: they are simply not listed)
+    std::vector<int> work;
+    for (int x : order) if (!(pairs[begin + x].flags & TWL_PAIR_PROFILE_ONLY)) work.push_back(x);
+    std::vector<DevResult> res(n);
+    for (auto &r : res) { r.status = 0; r.pathLen = 0; r.tiles = 0; r.pad = 0; r.cells = 0; r.diagonals = 0; }
+    std::vector<int8_t> hostPaths(std::max<size_t>(pathBytes, 1));
+    std::vector<std::vector<int8_t>> finalPath(n);
+    std::vector<int32_t> hRuns(std::max<size_t>(runInts, 2));
+    std::vector<char> hCons(std::max<size_t>(consBytes, 1));
+    bool first = true;
+    while (!work.empty()) {
+        const int nw = static_cast<int>(work.size());
+        TWL_CUDA(ctx, cudaMemcpyAsync(ctx->dOrder.ptr, work.data(), sizeof(int) * nw, cudaMemcpyHostToDevice, ctx->stream));
+        int rc = twlLaunchDpChain(ctx, nw, maxF);
+        if (rc != TWL_OK) return rc;
+        if (first) TWL_CUDA(ctx, cudaEventRecord(L->ev[3], ctx->stream));
+        TWL_CUDA(ctx, cudaMemcpyAsync(res.data(), ctx->dResults.ptr, sizeof(DevResult) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        TWL_CUDA(ctx, cudaMemcpyAsync(hostPaths.data(), ctx->dPaths.ptr, pathBytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (first) {
+            TWL_CUDA(ctx, cudaMemcpyAsync(sides.data(), L->dSides.ptr, sizeof(DevSide) * nSides, cudaMemcpyDeviceToHost, ctx->stream));
+            TWL_CUDA(ctx, cudaMemcpyAsync(hRuns.data(), L->dRuns.ptr, sizeof(int32_t) * runInts, cudaMemcpyDeviceToHost, ctx->stream));
+            TWL_CUDA(ctx, cudaMemcpyAsync(hCons.data(), L->dCons.ptr, consBytes, cudaMemcpyDeviceToHost, ctx->stream));
+            TWL_CUDA(ctx, cudaMemcpyAsync(dp.data(), ctx->dPairs.ptr, sizeof(DevPair) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        first = false;
+        std::vector<int> again;
+        for (int x : work) {
+            DevResult &r = res[x];
+            if (r.status == kStatusEmptySide) {   // alignment-cpu.cpp:89-90
+                r.status = 0;
+                finalPath[x].clear();
+                std::vector<int8_t> wo;
+                if (dp[x].refLen < 1) wo.assign(std::max(dp[x].qryLen, 0), 1);
+                else wo.assign(std::max(dp[x].refLen, 0), 2);
+                r.pathLen = static_cast<int>(wo.size());
+                std::memcpy(hostPaths.data() + dp[x].alnOff, wo.data(), wo.size());
+            }
+            if (r.status != 0 && task != 0) {     // retry ladder, alignment-cpu.cpp:116-129
+                if (r.status == 3) continue;
+                const int minLen = std::min(dp[x].refLen, dp[x].qryLen);
+                if (r.status == 2) dp[x].fLen = std::min(static_cast<int>(dp[x].fLen * 1.2) << 1, minLen);
+                else { dp[x].xdrop = dp[x].xdrop * 2; dp[x].fLen = std::min(static_cast<int>(dp[x].xdrop * 4) << 1, minLen); }
+                maxF = std::max(maxF, std::min(dp[x].fLen, minLen));
+                again.push_back(x);
+            }
+        }
+        if (!again.empty()) TWL_CUDA(ctx, cudaMemcpyAsync(ctx->dPairs.ptr, dp.data(), sizeof(DevPair) * n, cudaMemcpyHostToDevice, ctx->stream));
+        work.swap(again);
+    }
+    if (first) {   // nothing to align in this chunk: still need the side outputs
+        TWL_CUDA(ctx, cudaEventRecord(L->ev[3], ctx->stream));
+        TWL_CUDA(ctx, cudaMemcpyAsync(sides.data(), L->dSides.ptr, sizeof(DevSide) * nSides, cudaMemcpyDeviceToHost, ctx->stream));
+        TWL_CUDA(ctx, cudaMemcpyAsync(hRuns.data(), L->dRuns.ptr, sizeof(int32_t) * runInts, cudaMemcpyDeviceToHost, ctx->stream));
+        TWL_CUDA(ctx, cudaMemcpyAsync(hCons.data(), L->dCons.ptr, consBytes, cudaMemcpyDeviceToHost, ctx->stream));
+        TWL_CUDA(ctx, cudaMemcpyAsync(dp.data(), ctx->dPairs.ptr, sizeof(DevPair) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+
+    // ---- host: gappy columns back (helper.cpp:324-375), build the update list
+    std::vector<DevUpdate> ups;
+    std::vector<const char *> updIn;
+    std::vector<char *> updOut;
+    std::vector<int8_t> finalStage;
+    std::vector<int> updPair;
+    size_t chunkInts = 0, mergedWords = 0;
+    for (int p = 0; p < n; ++p) {
+        const twl_level_pair &in = pairs[begin + p];
+        twl_level_result &out = results[begin + p];
+        PairKeep &kp = L->keep[begin + p];
+        const DevSide &sr = sides[2 * p], &sq = sides[2 * p + 1];
+        for (int s = 0; s < 2; ++s) {
+            const DevSide &d = sides[2 * p + s];
+            kp.newLen[s] = d.newLen; kp.nRuns[s] = d.nRuns;
+            kp.runs[s].assign(hRuns.begin() + d.runsOff, hRuns.begin() + d.runsOff + 2 * d.nRuns);
+            kp.cons[s].assign(hCons.begin() + d.consOff, hCons.begin() + d.consOff + d.alnLen);
+        }
+        out.status = res[p].status; out.tiles = res[p].tiles; out.cells = res[p].cells; out.diagonals = res[p].diagonals;
+        out.ref_len_dp = sr.newLen; out.qry_len_dp = sq.newLen; out.path_len = 0;
+        out.cached = (sr.freqOutOff >= 0 ? 1 : 0) | (sq.freqOutOff >= 0 ? 2 : 0);
+        if (in.flags & TWL_PAIR_PROFILE_ONLY) { out.status = 0; continue; }
+        if (out.status != 0) continue;
+        kp.pathWo.assign(hostPaths.begin() + dp[p].alnOff, hostPaths.begin() + dp[p].alnOff + res[p].pathLen);
+        kp.pathWoLen = res[p].pathLen;
+        std::vector<int8_t> &fp = finalPath[p];
+        fp.clear();
+        restoreGappyColumns(type, ctx->hScore, ctx->M, ctx->gapOpen, ctx->gapExtend, kp.pathWo.data(), kp.pathWoLen, kp.runs[0].data(), sr.nRuns,
+                            kp.runs[1].data(), sq.nRuns, kp.cons[0].data(), kp.cons[1].data(), fp);
+        out.path_len = static_cast<int>(fp.size());
+        if (paths && paths[begin + p]) std::memcpy(paths[begin + p], fp.data(), fp.size());
+
+        DevUpdate u;
+        u.pathOff = static_cast<long long>(finalStage.size());
+        finalStage.insert(finalStage.end(), fp.begin(), fp.end());
+        finalStage.resize((finalStage.size() + 15) & ~static_cast<size_t>(15), 3);
+        u.chunkOff = static_cast<long long>(chunkInts);
+        chunkInts += 2 * ((fp.size() + kPathChunk - 1) / kPathChunk + 1);
+        u.memberOff = static_cast<long long>(updIn.size());
+        u.pathLen = out.path_len;
+        u.nRef = (task != 2) ? in.ref.n_ids : 0;                            // currentTask 2 only composes subtree paths (helper.cpp:384)
+        u.nQry = (task != 2) ? in.qry.n_ids : 0;
+        u.refWeight = in.ref.aln_weight; u.qryWeight = in.qry.aln_weight; u.pad = 0;
+        const twl_node_side *sd2[2] = {&in.ref, &in.qry};
+        for (int s = 0; s < 2; ++s) {
+            const int cnt = (s == 0) ? u.nRef : u.nQry;
+            for (int m = 0; m < cnt; ++m) {
+                RowSlot &r = L->rows[sd2[s]->seq_ids[m]];
+                if (r.cap < out.path_len) {                                 // SequenceInfo::memCheck, sequencedb.cpp:57-76
+                    const int cap = 2 * out.path_len;
+                    char *a0, *a1;
+                    TWL_CUDA(ctx, poolAlloc(L, cap, &a0));
+                    TWL_CUDA(ctx, poolAlloc(L, cap, &a1));
+                    // the live buffer keeps being read from its old place for this update; the new pair is used from now on
+                    updIn.push_back(r.buf[r.storage]);
+                    r.buf[0] = a0; r.buf[1] = a1; r.cap = cap;
+                    updOut.push_back(r.buf[1 - r.storage]);
+                } else {
+                    updIn.push_back(r.buf[r.storage]);
+                    updOut.push_back(r.buf[1 - r.storage]);
+                }
+                r.storage = 1 - r.storage;                                   // changeStorage()
+                r.len = out.path_len;
+            }
+        }
+        // updateFrequency applies when both nodes carry msaFreq after calculateProfile (helper.cpp:508)
+        const bool bothFreq = (sr.freqInOff >= 0 || sr.freqOutOff >= 0) && (sq.freqInOff >= 0 || sq.freqOutOff >= 0);
+        u.freqRefOff = u.freqQryOff = u.mergedOff = -1;
+        if (bothFreq) {
+            u.freqRefOff = (sr.freqInOff >= 0) ? sr.freqInOff : sr.freqOutOff;
+            u.freqQryOff = (sq.freqInOff >= 0) ? sq.freqInOff : sq.freqOutOff;
+            u.mergedOff = static_cast<long long>(mergedWords);
+            mergedWords += static_cast<size_t>(out.path_len) * P;
+            out.cached |= 4;
+        }
+        ups.push_back(u);
+        updPair.push_back(p);
+    }
+
+    // ---- phase 4: row update + frequency merge
+    if (!ups.empty()) {
+        const int nu = static_cast<int>(ups.size());
+        int maxPath = 0;
+        for (auto &u : ups) maxPath = std::max(maxPath, u.pathLen);
+        TWL_CUDA(ctx, L->dUps.reserve(nu));
+        TWL_CUDA(ctx, L->dFinalPaths.reserve(std::max<size_t>(finalStage.size(), 16)));
+        TWL_CUDA(ctx, L->dChunkCounts.reserve(std::max<size_t>(chunkInts, 2)));
+        TWL_CUDA(ctx, L->dRowIn.reserve(std::max<size_t>(updIn.size(), 1)));
+        TWL_CUDA(ctx, L->dRowOut.reserve(std::max<size_t>(updOut.size(), 1)));
+        TWL_CUDA(ctx, L->dMerged.reserve(std::max<size_t>(mergedWords, 1)));
+        TWL_CUDA(ctx, cudaMemcpyAsync(L->dUps.ptr, ups.data(), sizeof(DevUpdate) * nu, cudaMemcpyHostToDevice, ctx->stream));
+        TWL_CUDA(ctx, cudaMemcpyAsync(L->dFinalPaths.ptr, finalStage.data(), finalStage.size(), cudaMemcpyHostToDevice, ctx->stream));
+        if (!updIn.empty()) {
+            TWL_CUDA(ctx, cudaMemcpyAsync(L->dRowIn.ptr, updIn.data(), sizeof(char *) * updIn.size(), cudaMemcpyHostToDevice, ctx->stream));
+            TWL_CUDA(ctx, cudaMemcpyAsync(L->dRowOut.ptr, updOut.data(), sizeof(char *) * updOut.size(), cudaMemcpyHostToDevice, ctx->stream));
+        }
+        pathChunkKernel<<<(nu * 32 + 255) / 256, 256, 0, ctx->stream>>>(L->dUps.ptr, nu, L->dFinalPaths.ptr, L->dChunkCounts.ptr);
+        TWL_CUDA(ctx, cudaGetLastError());
+        dim3 grid(nu, std::max(1, (maxPath + kPathChunk - 1) / kPathChunk));
+        rowUpdateKernel<P><<<grid, kLvlThreads, 0, ctx->stream>>>(L->dUps.ptr, L->dFinalPaths.ptr, L->dChunkCounts.ptr, L->dRowIn.ptr, L->dRowOut.ptr,
+                                                              L->dFreq.ptr, L->dMerged.ptr);
+        TWL_CUDA(ctx, cudaGetLastError());
+        ctx->lastLaunches += 2;
+    }
+    TWL_CUDA(ctx, cudaEventRecord(L->ev[4], ctx->stream));
+
+    // ---- msaFreq results back to the host (only nodes >= cache threshold carry them)
+    std::vector<float> hFreq(freqWords), hMerged(mergedWords);
+    if (freqWords) TWL_CUDA(ctx, cudaMemcpyAsync(hFreq.data(), L->dFreq.ptr, sizeof(float) * freqWords, cudaMemcpyDeviceToHost, ctx->stream));
+    if (mergedWords) TWL_CUDA(ctx, cudaMemcpyAsync(hMerged.data(), L->dMerged.ptr, sizeof(float) * mergedWords, cudaMemcpyDeviceToHost, ctx->stream));
+    TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int p = 0; p < n; ++p) {
+        PairKeep &kp = L->keep[begin + p];
+        for (int s = 0; s < 2; ++s) {
+            const DevSide &d = sides[2 * p + s];
+            if (d.freqOutOff >= 0) kp.freq[s].assign(hFreq.begin() + d.freqOutOff, hFreq.begin() + d.freqOutOff + static_cast<size_t>(d.alnLen) * P);
+        }
+    }
+    for (size_t k = 0; k < ups.size(); ++k)
+        if (ups[k].mergedOff >= 0)
+            L->keep[begin + updPair[k]].merged.assign(hMerged.begin() + ups[k].mergedOff, hMerged.begin() + ups[k].mergedOff + static_cast<size_t>(ups[k].pathLen) * P);
+    for (int i = 0; i < 4; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, L->ev[i], L->ev[i + 1]);
+        L->phaseMs[i] += ms;
+    }
+    return TWL_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int twl_align_level(twl_ctx *ctx, const twl_level_pair *pairs, int n_pairs, int current_task, float gappy_threshold, int32_t cache_threshold,
+                    int8_t *const *paths, twl_level_result *results) {
+    if (!ctx) return TWL_E_ARG;
+    if (ctx->P == 0) return twlFail(ctx, TWL_E_STATE, "twl_align_level: call twl_set_params first");
+    if (n_pairs < 0 || (n_pairs > 0 && (!pairs || !results))) return twlFail(ctx, TWL_E_ARG, "twl_align_level: bad arguments");
+    TwlLevelState *L = levelOf(ctx);
+    cudaSetDevice(ctx->device);
+    ctx->lastLaunches = 0;
+    ctx->staged = false;   // the batch buffers are reused
+    ctx->ran = false;
+    L->keep.assign(n_pairs, PairKeep());
+    L->P = ctx->P;
+    for (float &m : L->phaseMs) m = 0.f;
+    if (cache_threshold <= 0) cache_threshold = 1000;
+    // chunk the level so that the scratch (raw profiles dominate: 4*P bytes per column and side) stays bounded
+    const size_t budget = static_cast<size_t>(12) << 30;
+    int begin = 0, chunkNo = 0;
+    while (begin < n_pairs) {
+        int end = begin;
+        size_t bytes = 0;
+        while (end < n_pairs) {
+            const size_t need = (static_cast<size_t>(pairs[end].ref.aln_len) + pairs[end].qry.aln_len) * (ctx->P * 4 + (ctx->P + 2) * 4 + 16) +
+                                (static_cast<size_t>(pairs[end].ref.n_ids) + pairs[end].qry.n_ids) * 24;
+            if (end > begin && bytes + need > budget) break;
+            bytes += need;
+            ++end;
+        }
+        const int rc = (ctx->P == 6) ? runLevelChunk<6>(ctx, L, pairs, begin, end, current_task, gappy_threshold, cache_threshold, paths, results, chunkNo)
+                                     : runLevelChunk<22>(ctx, L, pairs, begin, end, current_task, gappy_threshold, cache_threshold, paths, results, chunkNo);
+        if (rc != TWL_OK) return rc;
+        begin = end;
+        ++chunkNo;
+    }
+    L->lastChunks = chunkNo;
+    float total = 0.f;
+    for (float m : L->phaseMs) total += m;
+    ctx->lastMs = total;
+    ctx->timingPending = false;
+    return TWL_OK;
+}
+
+int twl_level_fetch(twl_ctx *ctx, int pair, int what, void *dst, size_t cap_bytes, size_t *out_bytes) {
+    if (!ctx || !ctx->level) return TWL_E_ARG;
+    TwlLevelState *L = ctx->level;
+    if (pair < 0 || static_cast<size_t>(pair) >= L->keep.size()) return twlFail(ctx, TWL_E_ARG, "twl_level_fetch: pair index out of range");
+    cudaSetDevice(ctx->device);
+    const PairKeep &kp = L->keep[pair];
+    const int P = L->P;
+    const void *src = nullptr;
+    size_t bytes = 0;
+    std::vector<float> tmp;
+    const int s = what & 1;
+    switch (what) {
+    case TWL_F_PROFILE_RAW_REF: case TWL_F_PROFILE_RAW_QRY: {
+        if (kp.chunk != L->lastChunks - 1) return twlFail(ctx, TWL_E_STATE, "twl_level_fetch: raw profiles are only kept for the last chunk of a level");
+        tmp.resize(static_cast<size_t>(kp.alnLen[s]) * P);
+        TWL_CUDA(ctx, cudaMemcpy(tmp.data(), L->dRaw.ptr + kp.rawOff[s], tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        src = tmp.data(); bytes = tmp.size() * sizeof(float);
+        break;
+    }
+    case TWL_F_DP_PROFILE_REF: case TWL_F_DP_PROFILE_QRY: {
+        if (kp.chunk != L->lastChunks - 1) return twlFail(ctx, TWL_E_STATE, "twl_level_fetch: packed profiles are only kept for the last chunk of a level");
+        const int len = kp.newLen[s], PW = P + 2;
+        const size_t words = (P == 6) ? static_cast<size_t>((len + 3) / 4) * 32 : static_cast<size_t>(len) * PW;
+        std::vector<float> packed(std::max<size_t>(words, 1));
+        TWL_CUDA(ctx, cudaMemcpy(packed.data(), ctx->dProf.ptr + kProfPadWords + kp.profOff[s], words * sizeof(float), cudaMemcpyDeviceToHost));
+        tmp.resize(static_cast<size_t>(len) * PW);
+        if (P == 6) {
+            const int n4 = (len + 3) / 4;
+            for (int c = 0; c < len; ++c) {
+                const float *x = packed.data() + twl::ntColIndex(c, n4) * 4, *y = x + static_cast<size_t>(16) * n4;
+                float *d = tmp.data() + static_cast<size_t>(c) * PW;
+                d[0] = x[0]; d[1] = x[1]; d[2] = x[2]; d[3] = x[3]; d[4] = y[0]; d[5] = y[1]; d[6] = y[2]; d[7] = y[3];
+            }
+        } else std::memcpy(tmp.data(), packed.data(), tmp.size() * sizeof(float));
+        src = tmp.data(); bytes = tmp.size() * sizeof(float);
+        break;
+    }
+    case TWL_F_CONSENSUS_REF: case TWL_F_CONSENSUS_QRY: src = kp.cons[s].data(); bytes = kp.cons[s].size(); break;
+    case TWL_F_RUNS_REF: case TWL_F_RUNS_QRY: src = kp.runs[s].data(); bytes = kp.runs[s].size() * sizeof(int32_t); break;
+    case TWL_F_PATH_WO: src = kp.pathWo.data(); bytes = kp.pathWo.size(); break;
+    case TWL_F_FREQ_REF: src = kp.freq[0].data(); bytes = kp.freq[0].size() * sizeof(float); break;
+    case TWL_F_FREQ_QRY: src = kp.freq[1].data(); bytes = kp.freq[1].size() * sizeof(float); break;
+    case TWL_F_FREQ_MERGED: src = kp.merged.data(); bytes = kp.merged.size() * sizeof(float); break;
+    default: return twlFail(ctx, TWL_E_ARG, "twl_level_fetch: unknown selector");
+    }
+    if (out_bytes) *out_bytes = bytes;
+    if (dst) {
+        if (bytes > cap_bytes) return twlFail(ctx, TWL_E_ARG, "twl_level_fetch: destination too small");
+        if (bytes) std::memcpy(dst, src, bytes);
+    }
+    return TWL_OK;
+}
+
+} // extern "C"
+
