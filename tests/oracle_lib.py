@@ -152,3 +152,52 @@ def ref_talco(cfg, fr, fq, gor, ger, goq, geq, ref_num, qry_num):
                             cfg.score, cfg.gap_open, cfg.gap_extend, cfg.gap_boundary, cfg.gap_char, cfg.xdrop, cfg.flen,
                             cfg.marker, aln, C.byref(err))
     return aln[:n].copy(), err.value
+
+
+def ref_pipeline(type_, cfg, ref_state, qry_state, gappy=0.95, current_task=0):
+    """Runs the UNMODIFIED reference helpers (alignment_helper::calculateProfile, getConsensus, removeGappyColumns,
+    calculatePSGP, Talco_xdrop::Align_freq, addGappyColumnsBack, updateFrequency, updateAlignment) on one pair through
+    oracle/ref_shim.cpp::ref_pair_pipeline and returns every intermediate as a dict. `*_state` are tests.ref_msa.NodeState."""
+    lib = ref()
+    P = cfg.P
+    nR, nQ = len(ref_state.rows), len(qry_state.rows)
+    RL, QL = ref_state.aln_len, qry_state.aln_len
+    mem, cap = max(RL, QL), RL + QL
+    rows_r = (C.c_char_p * max(nR, 1))(*ref_state.rows)
+    rows_q = (C.c_char_p * max(nQ, 1))(*qry_state.rows)
+    w_r = np.ascontiguousarray(ref_state.weights, np.float32)
+    w_q = np.ascontiguousarray(qry_state.weights, np.float32)
+    f_r = None if ref_state.msa_freq is None else np.ascontiguousarray(ref_state.msa_freq, np.float32)
+    f_q = None if qry_state.msa_freq is None else np.ascontiguousarray(qry_state.msa_freq, np.float32)
+    out = dict(profile_raw=np.zeros((2, mem, P), np.float32), consensus=C.create_string_buffer(2 * mem + 1),
+               profile=np.zeros((2, mem, P), np.float32), lens=np.zeros(2, np.int32), runs=np.zeros((2, mem, 2), np.int32),
+               n_runs=np.zeros(2, np.int32), gap_op=np.zeros((2, mem), np.float32), gap_ex=np.zeros((2, mem), np.float32),
+               aln_wo=np.zeros(cap + 1, np.int8), aln_w=np.zeros(cap + 1, np.int8), new_rows=C.create_string_buffer((nR + nQ) * cap + 1),
+               cached=np.zeros((2, mem, P), np.float32), cached_flag=np.zeros(2, np.int32), merged=np.zeros((cap + 1, P), np.float32))
+    n_wo, n_w, err, new_len, merged_flag = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+    fn = lib.ref_pair_pipeline
+    fn.restype = C.c_int
+    vp = C.c_void_p
+    fn.argtypes = [C.c_char, C.c_int, C.c_float, f32p, C.c_float, C.c_float, C.c_float, C.c_int,
+                   C.c_int, C.POINTER(C.c_char_p), f32p, C.c_int, C.c_int, C.c_float, vp,
+                   C.c_int, C.POINTER(C.c_char_p), f32p, C.c_int, C.c_int, C.c_float, vp,
+                   f32p, C.c_char_p, f32p, i32p, i32p, i32p, f32p, f32p, i8p, C.POINTER(C.c_int), i8p, C.POINTER(C.c_int),
+                   C.POINTER(C.c_int), C.c_char_p, C.POINTER(C.c_int), f32p, i32p, f32p, C.POINTER(C.c_int)]
+    fn(type_.encode(), current_task, gappy, cfg.score, cfg.gap_open, cfg.gap_extend, cfg.gap_boundary, cfg.marker,
+       nR, rows_r, w_r, RL, ref_state.aln_num, ref_state.aln_weight, None if f_r is None else f_r.ctypes.data,
+       nQ, rows_q, w_q, QL, qry_state.aln_num, qry_state.aln_weight, None if f_q is None else f_q.ctypes.data,
+       out["profile_raw"], out["consensus"], out["profile"], out["lens"], out["runs"], out["n_runs"], out["gap_op"], out["gap_ex"],
+       out["aln_wo"], C.byref(n_wo), out["aln_w"], C.byref(n_w), C.byref(err), out["new_rows"], C.byref(new_len), out["cached"],
+       out["cached_flag"], out["merged"], C.byref(merged_flag))
+    res = dict(error=err.value, aln_wo=out["aln_wo"][:n_wo.value].copy(), aln_w=out["aln_w"][:n_w.value].copy(), lens=out["lens"].copy(),
+               profile_raw=[out["profile_raw"][0, :RL].copy(), out["profile_raw"][1, :QL].copy()],
+               consensus=[out["consensus"].raw[:RL], out["consensus"].raw[mem:mem + QL]],
+               profile=[out["profile"][0, :out["lens"][0]].copy(), out["profile"][1, :out["lens"][1]].copy()],
+               gap_op=[out["gap_op"][0, :out["lens"][0]].copy(), out["gap_op"][1, :out["lens"][1]].copy()],
+               gap_ex=[out["gap_ex"][0, :out["lens"][0]].copy(), out["gap_ex"][1, :out["lens"][1]].copy()],
+               runs=[out["runs"][0, :out["n_runs"][0]].copy(), out["runs"][1, :out["n_runs"][1]].copy()],
+               new_len=new_len.value, merged=out["merged"][:new_len.value].copy() if merged_flag.value else None,
+               cached=[out["cached"][0, :RL].copy() if out["cached_flag"][0] else None, out["cached"][1, :QL].copy() if out["cached_flag"][1] else None])
+    raw = out["new_rows"].raw
+    res["new_rows"] = [raw[k * cap:k * cap + new_len.value] for k in range(nR + nQ)] if n_w.value else []
+    return res

@@ -46,3 +46,72 @@ def test_reference_cli_reproduces_golden(tmp_path):
     for name in ("rnasim_merge_msas", "rnasim_sub_prune"):
         out, _ = run_cli(ol.REF_CLI, name, str(tmp_path))
         assert hashlib.md5(open(out, "rb").read()).hexdigest() == gold[name]["md5"]
+
+
+@needs_ref
+@pytest.mark.parametrize("n,L,seed,marker,gappy", [(10, 400, 5, 1024, 0.95), (24, 600, 1, 256, 0.6), (14, 500, 8, 64, 0.8)])
+def test_port_level_functions_equal_reference_helpers(n, L, seed, marker, gappy):
+    """calculateProfile / getConsensus / removeGappyColumns / calculatePSGP / addGappyColumnsBack / updateAlignment of the
+    port against the unmodified alignment-helper.cpp on every merge of a synthetic tree."""
+    import copy
+    from twilight_b200 import synth
+    tree = synth.random_tree(n, seed=seed, mean_blen=0.06)
+    seqs = synth.evolve(tree, L, seed=seed, indel_rate=0.08)
+    w = np.random.default_rng(seed + 1).uniform(0.5, 1.5, n).astype(np.float32)
+    cfg = ol.TalcoCfg(marker=marker)
+    state = {i: ref_msa.leaf_state(seqs[i], w[i]) for i in range(n)}
+    checked = 0
+    for level in synth.levels_bottom_up(tree):
+        for a, b, parent in level:
+            ra, rb = state.pop(a), state.pop(b)
+            want = ol.ref_pipeline("n", cfg, copy.deepcopy(ra), copy.deepcopy(rb), gappy)
+            rec = ref_msa.align_pair("n", cfg, ra, rb, gappy)
+            assert rec.error == want["error"] == 0
+            for s in (0, 1):
+                assert np.array_equal(rec.profile_raw[s], want["profile_raw"][s])
+                assert rec.consensus[s] == want["consensus"][s]
+                assert np.array_equal(rec.profile[s], want["profile"][s])
+                assert np.array_equal(rec.gap_op[s], want["gap_op"][s]) and np.array_equal(rec.gap_ex[s], want["gap_ex"][s])
+                assert np.array_equal(np.asarray(rec.runs[s]).reshape(-1, 2), want["runs"][s])
+            assert np.array_equal(rec.aln_wo, want["aln_wo"])
+            assert np.array_equal(rec.aln_w, want["aln_w"])
+            assert rec.merged.rows == want["new_rows"]
+            state[parent] = rec.merged
+            checked += 1
+    assert checked == n - 1
+
+
+@needs_ref
+def test_port_frequency_cache_and_merge_equal_reference():
+    """The >=1000-sequence branch (msaFreq cache, cached-profile path, updateFrequency) on two synthetic 1000-row nodes."""
+    rng = np.random.default_rng(3)
+    L = 120
+    anc = rng.choice(np.frombuffer(b"ACGU", np.uint8), L)
+
+    def family(nrows, shift):
+        rows = []
+        for _ in range(nrows):
+            s = anc.copy()
+            hit = rng.random(L) < 0.1
+            s[hit] = rng.choice(np.frombuffer(b"ACGU-", np.uint8), int(hit.sum()))
+            rows.append(np.roll(s, shift).tobytes())
+        wts = rng.uniform(0.5, 1.5, nrows).astype(np.float32)
+        return ref_msa.NodeState(rows, wts, L, nrows, float(np.sum(wts, dtype=np.float32)))
+    a, b = family(1000, 0), family(3, 1)
+    cfg = ol.TalcoCfg()
+    import copy
+    want = ol.ref_pipeline("n", cfg, copy.deepcopy(a), copy.deepcopy(b), 0.95)
+    rec = ref_msa.align_pair("n", cfg, a, b, 0.95)
+    assert want["cached"][0] is not None and want["cached"][1] is not None and want["merged"] is not None
+    assert np.array_equal(rec.profile_raw[0], want["profile_raw"][0])
+    assert np.array_equal(rec.ref.msa_freq, want["cached"][0]) and np.array_equal(rec.qry.msa_freq, want["cached"][1])
+    assert np.array_equal(rec.aln_w, want["aln_w"])
+    assert np.array_equal(rec.merged.msa_freq, want["merged"])
+    # second merge: cached-profile branch on the ref side
+    c = family(2, 0)
+    m = rec.merged
+    want2 = ol.ref_pipeline("n", cfg, copy.deepcopy(m), copy.deepcopy(c), 0.95)
+    rec2 = ref_msa.align_pair("n", cfg, m, c, 0.95)
+    assert np.array_equal(rec2.profile_raw[0], want2["profile_raw"][0])
+    assert np.array_equal(rec2.aln_w, want2["aln_w"])
+    assert np.array_equal(rec2.merged.msa_freq, want2["merged"])
