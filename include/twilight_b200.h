@@ -117,10 +117,11 @@ typedef struct {
 
 typedef struct {
     twl_node_side ref, qry;
-    int32_t flags;              /* TWL_PAIR_PROFILE_ONLY: run calculateProfile (and its msaFreq caching) but no alignment */
+    int32_t flags;              /* TWL_PAIR_PROFILE_ONLY: run calculateProfile (and its msaFreq caching) but no alignment; TWL_PAIR_NO_ROW_UPDATE */
     int32_t reserved;
 } twl_level_pair;
 #define TWL_PAIR_PROFILE_ONLY 1
+#define TWL_PAIR_NO_ROW_UPDATE 2   /* align and merge msaFreq but leave the rows untouched (PLACE_WO_TREE, merge of sub-alignments) */
 
 typedef struct {
     int32_t status;             /* TWL_ST_*; rows are rewritten only when 0 */

@@ -493,8 +493,9 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
         chunkInts += 2 * ((fp.size() + kPathChunk - 1) / kPathChunk + 1);
         u.memberOff = static_cast<long long>(updIn.size());
         u.pathLen = out.path_len;
-        u.nRef = (task != 2) ? in.ref.n_ids : 0;                            // currentTask 2 only composes subtree paths (helper.cpp:384)
-        u.nQry = (task != 2) ? in.qry.n_ids : 0;
+        const bool touchRows = (task != 2) && !(in.flags & TWL_PAIR_NO_ROW_UPDATE);   // currentTask 2 only composes subtree paths (helper.cpp:384)
+        u.nRef = touchRows ? in.ref.n_ids : 0;
+        u.nQry = touchRows ? in.qry.n_ids : 0;
         u.refWeight = in.ref.aln_weight; u.qryWeight = in.qry.aln_weight; u.pad = 0;
         const twl_node_side *sd2[2] = {&in.ref, &in.qry};
         for (int s = 0; s < 2; ++s) {

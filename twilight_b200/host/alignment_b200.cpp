@@ -28,6 +28,8 @@ namespace msa {
 namespace progressive {
 namespace b200 {
 
+void alignmentKernel_B200(Tree *tree, NodePairVec &nodes, SequenceDB *database, Option *option, Params &param);
+
 namespace {
 
 struct Device {
@@ -242,6 +244,218 @@ void alignmentKernel_B200(Tree *tree, NodePairVec &nodes, SequenceDB *database, 
     alignment_helper::fallback2cpu(fallbackPairs, nodes, database, option);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Level pipeline: the whole per-pair body of parallelAlignmentCPU on the device through twl_align_level. Rows live in
+// HBM (twl_rows_*); the host SequenceDB is kept in sync after every level (rows are copied back into
+// SequenceInfo::alnStorage exactly where updateAlignment would have written them), so every other part of the host
+// (final write-out, storeSubtreeProfile, --check, parked-sequence materialisation) keeps working unchanged.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct Resident {            // what the device holds for a row id, to detect rows the host replaced (new subtree, new DB)
+    const void *owner = nullptr;
+    int len = -1;
+    bool storage = false;
+    uint64_t sig = 0;        // content signature of the host copy the device row corresponds to
+};
+
+// 64-bit multiplicative hash over the row bytes (one pass, 8 bytes per step)
+uint64_t rowSignature(const char *p, int len) {
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ static_cast<uint64_t>(len);
+    int k = 0;
+    for (; k + 8 <= len; k += 8) {
+        uint64_t w;
+        std::memcpy(&w, p + k, 8);
+        h = (h ^ w) * 0xFF51AFD7ED558CCDull;
+        h ^= h >> 29;
+    }
+    uint64_t tail = 0;
+    if (k < len) std::memcpy(&tail, p + k, len - k);
+    h = (h ^ tail) * 0xC4CEB9FE1A85EC53ull;
+    return h ^ (h >> 32);
+}
+std::vector<Resident> &resident() {
+    static std::vector<Resident> r;
+    return r;
+}
+
+void flatten(const Profile &f, std::vector<float> &out) {
+    out.clear();
+    for (const auto &col : f) out.insert(out.end(), col.begin(), col.end());
+}
+
+void unflatten(const std::vector<float> &in, int P, Profile &f) {
+    const size_t n = in.size() / P;
+    f.assign(n, std::vector<float>(P, 0.f));
+    for (size_t t = 0; t < n; ++t)
+        for (int v = 0; v < P; ++v) f[t][v] = in[t * P + v];
+}
+
+bool fetchFreq(twl_ctx *ctx, int pair, int what, std::vector<float> &out) {
+    size_t bytes = 0;
+    if (twl_level_fetch(ctx, pair, what, nullptr, 0, &bytes) != TWL_OK) return false;
+    out.resize(bytes / sizeof(float));
+    return twl_level_fetch(ctx, pair, what, out.data(), bytes, &bytes) == TWL_OK;
+}
+
+} // namespace
+
+void alignmentKernel_B200_level(Tree *tree, NodePairVec &nodes, SequenceDB *database, Option *option, Params &param) {
+    ensureContext(param);
+    twl_ctx *ctx = device().ctx;
+    const int P = param.matrixSize + 1;
+    const int task = database->currentTask;
+    const int nPairs = static_cast<int>(nodes.size());
+
+    // levels with empty nodes take the profile-batch path (alignment-cpu.cpp:89-90 special case)
+    for (auto &pr : nodes)
+        if (pr.first->getAlnLen(task) == 0 || pr.second->getAlnLen(task) == 0) { alignmentKernel_B200(tree, nodes, database, option, param); return; }
+
+    std::vector<twl_level_pair> lp(nPairs);
+    std::vector<std::vector<int32_t>> ids(2 * nPairs);
+    std::vector<std::vector<float>> freqs(2 * nPairs);
+    std::vector<char> lowQ(nPairs, 0);
+    const bool updateRows = (option->alnMode != PLACE_WO_TREE) && (task != 2);
+
+    // rows that must be (re)sent: unknown to the device or replaced on the host since
+    std::vector<int32_t> upIds, upLens;
+    std::vector<const char *> upRows;
+    std::vector<float> upW;
+    auto &res = resident();
+    for (int n = 0; n < nPairs; ++n) {
+        Node *nd[2] = {nodes[n].first, nodes[n].second};
+        twl_node_side *side[2] = {&lp[n].ref, &lp[n].qry};
+        for (int s = 0; s < 2; ++s) {
+            auto &v = ids[2 * n + s];
+            const bool cached = !nd[s]->msaFreq.empty();
+            for (int sIdx : nd[s]->seqsIncluded) {
+                if (sIdx < 0) continue;                                    // parked group / subtree id: path composition only
+                if (cached && !updateRows) continue;                       // rows neither read nor written
+                v.push_back(sIdx);
+                auto *seq = database->sequences[sIdx];
+                if (static_cast<size_t>(sIdx) >= res.size()) res.resize(sIdx + 1);
+                Resident &r = res[sIdx];
+                const uint64_t sig = rowSignature(seq->alnStorage[seq->storage], seq->len);
+                if (r.owner != seq || r.len != seq->len || r.storage != seq->storage || r.sig != sig) {
+                    upIds.push_back(sIdx); upLens.push_back(seq->len); upRows.push_back(seq->alnStorage[seq->storage]); upW.push_back(seq->weight);
+                    r.owner = seq; r.len = seq->len; r.storage = seq->storage; r.sig = sig;
+                }
+            }
+            if (cached) flatten(nd[s]->msaFreq, freqs[2 * n + s]);
+            side[s]->seq_ids = v.data();
+            side[s]->n_ids = static_cast<int32_t>(v.size());
+            side[s]->aln_len = nd[s]->getAlnLen(task);
+            side[s]->aln_num = nd[s]->getAlnNum(task);
+            side[s]->aln_weight = nd[s]->alnWeight;
+            side[s]->msa_freq = cached ? freqs[2 * n + s].data() : nullptr;
+        }
+        const int refNum = lp[n].ref.aln_num, qryNum = lp[n].qry.aln_num;
+        const bool lowQ_r = (option->alnMode == MERGE_MSA) ? false : ((refNum > 1) ? false : database->sequences[nodes[n].first->seqsIncluded[0]]->lowQuality);
+        const bool lowQ_q = (option->alnMode == MERGE_MSA) ? false : ((qryNum > 1) ? false : database->sequences[nodes[n].second->seqsIncluded[0]]->lowQuality);
+        lowQ[n] = lowQ_r || lowQ_q;
+        lp[n].flags = (lowQ[n] ? TWL_PAIR_PROFILE_ONLY : 0) | (updateRows ? 0 : TWL_PAIR_NO_ROW_UPDATE);
+        lp[n].reserved = 0;
+    }
+    if (!upIds.empty() && twl_rows_upload(ctx, static_cast<int>(upIds.size()), upIds.data(), upRows.data(), upLens.data(), upW.data()) != TWL_OK)
+        die("twl_rows_upload", twl_last_error(ctx));
+
+    std::vector<twl_level_result> out(nPairs);
+    std::vector<std::vector<int8_t>> pathBuf(nPairs);
+    std::vector<int8_t *> pathPtr(nPairs);
+    for (int n = 0; n < nPairs; ++n) {
+        pathBuf[n].resize(static_cast<size_t>(lp[n].ref.aln_len) + lp[n].qry.aln_len + 1);
+        pathPtr[n] = pathBuf[n].data();
+    }
+    if (twl_align_level(ctx, lp.data(), nPairs, task, option->gappyVertical, alignment_helper::_CAL_PROFILE_TH, pathPtr.data(), out.data()) != TWL_OK)
+        die("twl_align_level", twl_last_error(ctx));
+
+    std::vector<int> fallbackPairs;
+    std::vector<int32_t> downIds;
+    std::vector<char *> downDst;
+    for (int n = 0; n < nPairs; ++n) {
+        Node *first = nodes[n].first, *second = nodes[n].second;
+        std::vector<float> flat;
+        // calculateProfile's msaFreq cache (helper.cpp:35-40) happens whether or not the pair aligns
+        if ((out[n].cached & 1) && fetchFreq(ctx, n, TWL_F_FREQ_REF, flat)) unflatten(flat, P, first->msaFreq);
+        if ((out[n].cached & 2) && fetchFreq(ctx, n, TWL_F_FREQ_QRY, flat)) unflatten(flat, P, second->msaFreq);
+        const int refNum = lp[n].ref.aln_num, qryNum = lp[n].qry.aln_num;
+        if (!lowQ[n] && out[n].status != 0) {
+            if (out[n].status == 3) { std::cout << "There might be some bugs in the code!\n"; std::exit(1); }
+            fallbackPairs.push_back(n);                                    // only task 0 leaves a status behind (alignment-cpu.cpp:108-115)
+            continue;
+        }
+        if (lowQ[n]) {
+            if (task == 0 && (refNum == 1 || qryNum == 1)) fallbackPairs.push_back(n);   // :135-144
+            continue;
+        }
+        alnPath aln(pathBuf[n].begin(), pathBuf[n].begin() + out[n].path_len);
+        if (option->alnMode == PLACE_WO_TREE) {
+            database->subtreeAln[second->seqsIncluded[0]] = aln;          // :172-174
+            continue;
+        }
+        // updateFrequency, helper.cpp:506-539
+        if (!first->msaFreq.empty() && !second->msaFreq.empty()) {
+            if (!(out[n].cached & 4) || !fetchFreq(ctx, n, TWL_F_FREQ_MERGED, flat)) die("twl_level_fetch", "merged msaFreq missing");
+            second->msaFreq.clear();
+            unflatten(flat, P, first->msaFreq);
+            first->alnLen = static_cast<int>(first->msaFreq.size());
+        }
+        // updateAlignment, helper.cpp:377-503: resident rows were rewritten on the device; mirror them into the host DB
+        const int totalLen = static_cast<int>(aln.size());
+        Node *nd[2] = {first, second};
+        for (int s = 0; s < 2; ++s) {
+            const int8_t own = (s == 0) ? 2 : 1;
+            for (int sIdx : nd[s]->seqsIncluded) {
+                if (task != 2 && sIdx >= 0) {
+                    auto *seq = database->sequences[sIdx];
+                    seq->memCheck(totalLen);
+                    downIds.push_back(sIdx);
+                    downDst.push_back(seq->alnStorage[1 - seq->storage]);
+                    seq->len = totalLen;
+                    seq->changeStorage();
+                    Resident &r = res[sIdx];
+                    r.owner = seq; r.len = totalLen; r.storage = seq->storage;
+                } else {
+                    alnPath &org = database->subtreeAln[sIdx];
+                    alnPath updated(aln.size());
+                    int orgIdx = 0;
+                    for (size_t k = 0; k < aln.size(); ++k) updated[k] = (aln[k] == 0 || aln[k] == own) ? org[orgIdx++] : static_cast<int8_t>(1);
+                    org = updated;
+                }
+            }
+        }
+        first->alnNum += second->alnNum;
+        first->alnLen = totalLen;
+        first->alnWeight += second->alnWeight;
+        for (auto idx : second->seqsIncluded) first->seqsIncluded.push_back(idx);
+        second->seqsIncluded.clear();
+        // parking of >1000 sequences behind one group id, helper.cpp:479-500
+        if (first->seqsIncluded.size() > alignment_helper::_UPDATE_SEQ_TH && !first->msaFreq.empty() && task != 2) {
+            int seqCount = 0, firstSeqID = 0;
+            for (auto idx : first->seqsIncluded)
+                if (idx > 1) { if (firstSeqID == 0) firstSeqID = -idx; seqCount++; }
+            if (seqCount >= alignment_helper::_UPDATE_SEQ_TH) {
+                database->subtreeAln[firstSeqID] = alnPath(totalLen, 0);
+                std::vector<int> kept;
+                kept.push_back(firstSeqID);
+                for (auto idx : first->seqsIncluded) {
+                    if (idx >= 0) database->sequences[idx]->subtreeIdx = firstSeqID;
+                    else kept.push_back(idx);
+                }
+                first->seqsIncluded = kept;
+            }
+        }
+    }
+    if (!downIds.empty() && twl_rows_download(ctx, static_cast<int>(downIds.size()), downIds.data(), downDst.data(), nullptr) != TWL_OK)
+        die("twl_rows_download", twl_last_error(ctx));
+    for (int32_t id : downIds) {
+        auto *seq = database->sequences[id];
+        res[id].sig = rowSignature(seq->alnStorage[seq->storage], seq->len);
+    }
+    if (fallbackPairs.empty()) return;
+    alignment_helper::fallback2cpu(fallbackPairs, nodes, database, option);
+}
+
 } // namespace b200
 
 // Build-time hook used by the drop-in CLI (twilight_b200/host/Makefile): the unchanged twilight-main.cpp and
@@ -249,7 +463,11 @@ void alignmentKernel_B200(Tree *tree, NodePairVec &nodes, SequenceDB *database, 
 // reference passes cpu::alignmentKernel_CPU resolves to this symbol instead.
 namespace cpu {
 void alignmentKernel_B200_entry(Tree *T, NodePairVec &alnPairs, SequenceDB *database, Option *option, Params &param) {
-    b200::alignmentKernel_B200(T, alnPairs, database, option, param);
+    // TWL_PIPELINE=dp keeps profile preparation and row update on the host (reference helpers) and runs only the DP on
+    // the device; the default runs the whole per-pair pipeline on the device.
+    static const bool dpOnly = [] { const char *e = std::getenv("TWL_PIPELINE"); return e && std::string(e) == "dp"; }();
+    if (dpOnly) b200::alignmentKernel_B200(T, alnPairs, database, option, param);
+    else b200::alignmentKernel_B200_level(T, alnPairs, database, option, param);
 }
 } // namespace cpu
 
