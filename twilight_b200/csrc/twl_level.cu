@@ -46,7 +46,7 @@ struct TwlLevelState {
     DevBuf<int8_t> dFinalPaths;
     DevBuf<signed char> dAaLut;
     bool lutReady = false;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float phaseMs[4] = {0, 0, 0, 0};
 
     std::vector<PairKeep> keep;
@@ -534,6 +534,7 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
     }
 
     // ---- phase 4: row update + frequency merge
+    bool updateTimed = false;
     if (!ups.empty()) {
         const int nu = static_cast<int>(ups.size());
         int maxPath = 0;
@@ -550,6 +551,8 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
             TWL_CUDA(ctx, cudaMemcpyAsync(L->dRowIn.ptr, updIn.data(), sizeof(char *) * updIn.size(), cudaMemcpyHostToDevice, ctx->stream));
             TWL_CUDA(ctx, cudaMemcpyAsync(L->dRowOut.ptr, updOut.data(), sizeof(char *) * updOut.size(), cudaMemcpyHostToDevice, ctx->stream));
         }
+        TWL_CUDA(ctx, cudaEventRecord(L->ev[5], ctx->stream));
+        updateTimed = true;
         pathChunkKernel<<<(nu * 32 + 255) / 256, 256, 0, ctx->stream>>>(L->dUps.ptr, nu, L->dFinalPaths.ptr, L->dChunkCounts.ptr);
         TWL_CUDA(ctx, cudaGetLastError());
         dim3 grid(nu, std::max(1, (maxPath + kPathChunk - 1) / kPathChunk));
@@ -575,10 +578,15 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
     for (size_t k = 0; k < ups.size(); ++k)
         if (ups[k].mergedOff >= 0)
             L->keep[begin + updPair[k]].merged.assign(hMerged.begin() + ups[k].mergedOff, hMerged.begin() + ups[k].mergedOff + static_cast<size_t>(ups[k].pathLen) * P);
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 3; ++i) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, L->ev[i], L->ev[i + 1]);
         L->phaseMs[i] += ms;
+    }
+    if (updateTimed) {   // the stream idles between the DP and the update while the host restores gappy columns
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, L->ev[5], L->ev[4]);
+        L->phaseMs[3] += ms;
     }
     return TWL_OK;
 }
