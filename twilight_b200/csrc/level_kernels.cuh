@@ -109,6 +109,29 @@ __global__ void __launch_bounds__(kLvlThreads) profileBuildKernel(const DevSide 
     cons[sd.consOff + t] = lut[best];
 }
 
+// Batched row transfers: rows sit at arbitrary places of the row pools, the host side of a transfer is one tightly packed
+// staging buffer. One warp copies one row (16-byte vectors when both ends allow it).
+struct RowCopy {
+    char *dev;          // the row inside a pool
+    long long stageOff; // its place in the staging buffer
+    int len, pad;
+};
+__global__ void rowTransferKernel(const RowCopy *list, int n, char *stage, int toDevice) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const RowCopy rc = list[w];
+    char *a = rc.dev, *b = stage + rc.stageOff;
+    char *dst = toDevice ? a : b;
+    const char *src = toDevice ? b : a;
+    if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0) {
+        const int n16 = rc.len >> 4;
+        for (int k = lane; k < n16; k += 32) reinterpret_cast<uint4 *>(dst)[k] = reinterpret_cast<const uint4 *>(src)[k];
+        for (int k = (n16 << 4) + lane; k < rc.len; k += 32) dst[k] = src[k];
+    } else {
+        for (int k = lane; k < rc.len; k += 32) dst[k] = src[k];
+    }
+}
+
 // block-wide exclusive scan of one int per thread (kLvlThreads threads); returns the exclusive prefix, total in *total
 __device__ __forceinline__ int blockExclusiveScan(int v, int *warpSums, int *total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

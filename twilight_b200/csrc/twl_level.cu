@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstring>
 #include <numeric>
+#include <thread>
 
 namespace {
 
@@ -45,6 +46,9 @@ struct TwlLevelState {
     DevBuf<twl::DevUpdate> dUps;
     DevBuf<int8_t> dFinalPaths;
     DevBuf<signed char> dAaLut;
+    DevBuf<twl::RowCopy> dCopies;
+    DevBuf<char> dStage;
+    PinBuf<char> hStage;
     bool lutReady = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float phaseMs[4] = {0, 0, 0, 0};
@@ -164,7 +168,7 @@ void twlLevelDestroy(twl_ctx *ctx) {
     for (void *p : L->pools) cudaFree(p);
     L->dSides.release(); L->dRowIn.release(); L->dRowOut.release(); L->dRowW.release(); L->dRaw.release(); L->dFreq.release();
     L->dMerged.release(); L->dCons.release(); L->dRuns.release(); L->dChunkCounts.release(); L->dUps.release();
-    L->dFinalPaths.release(); L->dAaLut.release();
+    L->dFinalPaths.release(); L->dAaLut.release(); L->dCopies.release(); L->dStage.release(); L->hStage.release();
     for (auto &e : L->ev) if (e) cudaEventDestroy(e);
     delete L;
     ctx->level = nullptr;
@@ -190,15 +194,11 @@ int twl_rows_upload(twl_ctx *ctx, int n, const int32_t *ids, const char *const *
     if (n < 0 || (n > 0 && (!ids || !rows || !lens || !weights))) return twlFail(ctx, TWL_E_ARG, "twl_rows_upload: null argument");
     TwlLevelState *L = levelOf(ctx);
     cudaSetDevice(ctx->device);
+    if (n == 0) return TWL_OK;
+    std::vector<twl::RowCopy> list(n);
     size_t total = 0;
     for (int i = 0; i < n; ++i) {
         if (ids[i] < 0 || lens[i] < 0) return twlFail(ctx, TWL_E_ARG, "twl_rows_upload: negative id or length");
-        total += (static_cast<size_t>(lens[i]) + 15) & ~static_cast<size_t>(15);
-    }
-    PinBuf<char> stage;
-    TWL_CUDA(ctx, stage.reserve(std::max<size_t>(total, 16)));
-    size_t at = 0;
-    for (int i = 0; i < n; ++i) {
         const int id = ids[i];
         if (static_cast<size_t>(id) >= L->rows.size()) L->rows.resize(id + 1);
         RowSlot &r = L->rows[id];
@@ -209,12 +209,18 @@ int twl_rows_upload(twl_ctx *ctx, int n, const int32_t *ids, const char *const *
             r.cap = cap;
         }
         r.len = lens[i]; r.storage = 0; r.weight = weights[i]; r.present = true;
-        std::memcpy(stage.ptr + at, rows[i], lens[i]);
-        TWL_CUDA(ctx, cudaMemcpyAsync(r.buf[0], stage.ptr + at, lens[i], cudaMemcpyHostToDevice, ctx->stream));
-        at += (static_cast<size_t>(lens[i]) + 15) & ~static_cast<size_t>(15);
+        list[i].dev = r.buf[0]; list[i].stageOff = static_cast<long long>(total); list[i].len = lens[i]; list[i].pad = 0;
+        total += (static_cast<size_t>(lens[i]) + 15) & ~static_cast<size_t>(15);
     }
+    TWL_CUDA(ctx, L->hStage.reserve(std::max<size_t>(total, 16)));
+    TWL_CUDA(ctx, L->dStage.reserve(std::max<size_t>(total, 16)));
+    TWL_CUDA(ctx, L->dCopies.reserve(n));
+    for (int i = 0; i < n; ++i) std::memcpy(L->hStage.ptr + list[i].stageOff, rows[i], lens[i]);
+    TWL_CUDA(ctx, cudaMemcpyAsync(L->dStage.ptr, L->hStage.ptr, total, cudaMemcpyHostToDevice, ctx->stream));
+    TWL_CUDA(ctx, cudaMemcpyAsync(L->dCopies.ptr, list.data(), sizeof(twl::RowCopy) * n, cudaMemcpyHostToDevice, ctx->stream));
+    twl::rowTransferKernel<<<(n * 32 + 255) / 256, 256, 0, ctx->stream>>>(L->dCopies.ptr, n, L->dStage.ptr, 1);
+    TWL_CUDA(ctx, cudaGetLastError());
     TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    stage.release();
     return TWL_OK;
 }
 
@@ -228,29 +234,28 @@ int twl_rows_download(twl_ctx *ctx, int n, const int32_t *ids, char *const *dst,
     if (n < 0 || (n > 0 && (!ids || !dst))) return twlFail(ctx, TWL_E_ARG, "twl_rows_download: null argument");
     TwlLevelState *L = levelOf(ctx);
     cudaSetDevice(ctx->device);
+    if (n == 0) return TWL_OK;
+    std::vector<twl::RowCopy> list(n);
     size_t total = 0;
     for (int i = 0; i < n; ++i) {
         if (ids[i] < 0 || static_cast<size_t>(ids[i]) >= L->rows.size() || !L->rows[ids[i]].present)
             return twlFail(ctx, TWL_E_ARG, "twl_rows_download: unknown row id " + std::to_string(ids[i]));
-        total += (static_cast<size_t>(L->rows[ids[i]].len) + 15) & ~static_cast<size_t>(15);
-    }
-    PinBuf<char> stage;
-    TWL_CUDA(ctx, stage.reserve(std::max<size_t>(total, 16)));
-    size_t at = 0;
-    for (int i = 0; i < n; ++i) {
         const RowSlot &r = L->rows[ids[i]];
-        TWL_CUDA(ctx, cudaMemcpyAsync(stage.ptr + at, r.buf[r.storage], r.len, cudaMemcpyDeviceToHost, ctx->stream));
-        at += (static_cast<size_t>(r.len) + 15) & ~static_cast<size_t>(15);
+        list[i].dev = r.buf[r.storage]; list[i].stageOff = static_cast<long long>(total); list[i].len = r.len; list[i].pad = 0;
+        total += (static_cast<size_t>(r.len) + 15) & ~static_cast<size_t>(15);
     }
+    TWL_CUDA(ctx, L->hStage.reserve(std::max<size_t>(total, 16)));
+    TWL_CUDA(ctx, L->dStage.reserve(std::max<size_t>(total, 16)));
+    TWL_CUDA(ctx, L->dCopies.reserve(n));
+    TWL_CUDA(ctx, cudaMemcpyAsync(L->dCopies.ptr, list.data(), sizeof(twl::RowCopy) * n, cudaMemcpyHostToDevice, ctx->stream));
+    twl::rowTransferKernel<<<(n * 32 + 255) / 256, 256, 0, ctx->stream>>>(L->dCopies.ptr, n, L->dStage.ptr, 0);
+    TWL_CUDA(ctx, cudaGetLastError());
+    TWL_CUDA(ctx, cudaMemcpyAsync(L->hStage.ptr, L->dStage.ptr, total, cudaMemcpyDeviceToHost, ctx->stream));
     TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    at = 0;
     for (int i = 0; i < n; ++i) {
-        const RowSlot &r = L->rows[ids[i]];
-        std::memcpy(dst[i], stage.ptr + at, r.len);
-        if (lens) lens[i] = r.len;
-        at += (static_cast<size_t>(r.len) + 15) & ~static_cast<size_t>(15);
+        std::memcpy(dst[i], L->hStage.ptr + list[i].stageOff, list[i].len);
+        if (lens) lens[i] = list[i].len;
     }
-    stage.release();
     return TWL_OK;
 }
 
@@ -454,6 +459,47 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
     }
 
     // ---- host: gappy columns back (helper.cpp:324-375), build the update list
+    // (a) per pair, independent: restore the removed column runs -> final path (host threads)
+    std::vector<char> aligned(n, 0);
+    {
+        auto restoreRange = [&](int t, int nThreads) {
+            for (int p = t; p < n; p += nThreads) {
+                const twl_level_pair &in = pairs[begin + p];
+                twl_level_result &out = results[begin + p];
+                PairKeep &kp = L->keep[begin + p];
+                const DevSide &sr = sides[2 * p], &sq = sides[2 * p + 1];
+                for (int s = 0; s < 2; ++s) {
+                    const DevSide &d = sides[2 * p + s];
+                    kp.newLen[s] = d.newLen; kp.nRuns[s] = d.nRuns;
+                    kp.runs[s].assign(hRuns.begin() + d.runsOff, hRuns.begin() + d.runsOff + 2 * d.nRuns);
+                    kp.cons[s].assign(hCons.begin() + d.consOff, hCons.begin() + d.consOff + d.alnLen);
+                }
+                out.status = res[p].status; out.tiles = res[p].tiles; out.cells = res[p].cells; out.diagonals = res[p].diagonals;
+                out.ref_len_dp = sr.newLen; out.qry_len_dp = sq.newLen; out.path_len = 0;
+                out.cached = (sr.freqOutOff >= 0 ? 1 : 0) | (sq.freqOutOff >= 0 ? 2 : 0);
+                if (in.flags & TWL_PAIR_PROFILE_ONLY) { out.status = 0; continue; }
+                if (out.status != 0) continue;
+                kp.pathWo.assign(hostPaths.begin() + dp[p].alnOff, hostPaths.begin() + dp[p].alnOff + res[p].pathLen);
+                kp.pathWoLen = res[p].pathLen;
+                std::vector<int8_t> &fp = finalPath[p];
+                fp.clear();
+                restoreGappyColumns(type, ctx->hScore, ctx->M, ctx->gapOpen, ctx->gapExtend, kp.pathWo.data(), kp.pathWoLen, kp.runs[0].data(), sr.nRuns,
+                                    kp.runs[1].data(), sq.nRuns, kp.cons[0].data(), kp.cons[1].data(), fp);
+                out.path_len = static_cast<int>(fp.size());
+                if (paths && paths[begin + p]) std::memcpy(paths[begin + p], fp.data(), fp.size());
+                aligned[p] = 1;
+            }
+        };
+        const int nThreads = (n >= 64) ? static_cast<int>(std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()))) : 1;
+        if (nThreads == 1) restoreRange(0, 1);
+        else {
+            std::vector<std::thread> pool;
+            for (int t = 1; t < nThreads; ++t) pool.emplace_back(restoreRange, t, nThreads);
+            restoreRange(0, nThreads);
+            for (auto &th : pool) th.join();
+        }
+    }
+    // (b) serial: the update list
     std::vector<DevUpdate> ups;
     std::vector<const char *> updIn;
     std::vector<char *> updOut;
@@ -461,29 +507,11 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
     std::vector<int> updPair;
     size_t chunkInts = 0, mergedWords = 0;
     for (int p = 0; p < n; ++p) {
+        if (!aligned[p]) continue;
         const twl_level_pair &in = pairs[begin + p];
         twl_level_result &out = results[begin + p];
-        PairKeep &kp = L->keep[begin + p];
         const DevSide &sr = sides[2 * p], &sq = sides[2 * p + 1];
-        for (int s = 0; s < 2; ++s) {
-            const DevSide &d = sides[2 * p + s];
-            kp.newLen[s] = d.newLen; kp.nRuns[s] = d.nRuns;
-            kp.runs[s].assign(hRuns.begin() + d.runsOff, hRuns.begin() + d.runsOff + 2 * d.nRuns);
-            kp.cons[s].assign(hCons.begin() + d.consOff, hCons.begin() + d.consOff + d.alnLen);
-        }
-        out.status = res[p].status; out.tiles = res[p].tiles; out.cells = res[p].cells; out.diagonals = res[p].diagonals;
-        out.ref_len_dp = sr.newLen; out.qry_len_dp = sq.newLen; out.path_len = 0;
-        out.cached = (sr.freqOutOff >= 0 ? 1 : 0) | (sq.freqOutOff >= 0 ? 2 : 0);
-        if (in.flags & TWL_PAIR_PROFILE_ONLY) { out.status = 0; continue; }
-        if (out.status != 0) continue;
-        kp.pathWo.assign(hostPaths.begin() + dp[p].alnOff, hostPaths.begin() + dp[p].alnOff + res[p].pathLen);
-        kp.pathWoLen = res[p].pathLen;
         std::vector<int8_t> &fp = finalPath[p];
-        fp.clear();
-        restoreGappyColumns(type, ctx->hScore, ctx->M, ctx->gapOpen, ctx->gapExtend, kp.pathWo.data(), kp.pathWoLen, kp.runs[0].data(), sr.nRuns,
-                            kp.runs[1].data(), sq.nRuns, kp.cons[0].data(), kp.cons[1].data(), fp);
-        out.path_len = static_cast<int>(fp.size());
-        if (paths && paths[begin + p]) std::memcpy(paths[begin + p], fp.data(), fp.size());
 
         DevUpdate u;
         u.pathOff = static_cast<long long>(finalStage.size());

@@ -223,3 +223,35 @@ def profile_pair_batch(n_pairs: int, length: int, seed: int = 0, kind: str = "rn
         out.append(dict(freq_ref=fr, freq_qry=fq, gap_open_ref=gor, gap_ext_ref=ger, gap_open_qry=goq, gap_ext_qry=geq,
                         ref_num=nr, qry_num=nq))
     return out
+
+
+def family_rows(anc: np.ndarray, members: int, rng, kind: str, sub_rate=0.08, del_rate=0.02):
+    """`members` aligned rows (bytes, '-' for deletions) derived from one ancestor; all rows have len(anc) columns."""
+    alphabet = {"rna": RNA, "dna": NT, "protein": AA}[kind]
+    L = len(anc)
+    rows = []
+    for _ in range(members):
+        s = anc.copy()
+        hit = rng.random(L) < sub_rate
+        s[hit] = rng.choice(alphabet, size=int(hit.sum()))
+        if members > 1 and del_rate > 0:
+            for st in np.flatnonzero(rng.random(L) < del_rate / 3):
+                s[st:st + int(rng.geometric(0.4))] = ord("-")
+        rows.append(s.tobytes())
+    return rows
+
+
+def level_rows_batch(n_pairs: int, length: int, seed: int = 0, kind: str = "rna", members=(1, 2, 4, 8), divergence: float = 0.15,
+                     indel_rate: float = 0.03):
+    """A guide-tree-level-shaped batch at the row level: n_pairs sibling nodes, each node a small aligned family of
+    1-8 rows of ~`length` columns. Returns [(ref_rows, qry_rows), ...]."""
+    rng = np.random.default_rng(seed)
+    alphabet = {"rna": RNA, "dna": NT, "protein": AA}[kind]
+    probs = AA_FREQ / AA_FREQ.sum() if kind == "protein" else None
+    out = []
+    for _ in range(n_pairs):
+        root = rng.choice(alphabet, size=int(length * rng.uniform(0.97, 1.03)), p=probs)
+        a = _mutate(root, divergence / 2, rng, alphabet, indel_rate, probs)
+        b = _mutate(root, divergence / 2, rng, alphabet, indel_rate, probs)
+        out.append((family_rows(a, int(rng.choice(members)), rng, kind), family_rows(b, int(rng.choice(members)), rng, kind)))
+    return out
