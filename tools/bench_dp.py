@@ -1,18 +1,16 @@
 #!/usr/bin/env python
-"""bench.py — throughput of the per-level TALCO-XDrop alignment path on B200.
+"""tools/bench_dp.py — DP-only micro-benchmark (profiles in, paths out; twl_batch_stage/run/fetch). The contract bench is
+../bench.py; this one isolates the TALCO-XDrop kernel chain on pre-built profile pairs.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs P] [--length L] [--impl reference]
 
-A "step" is one pass of the hot path over one synthetic guide-tree level: 4096 node pairs per GPU, every node a small
-aligned family of 1-8 RNASim-shaped rows (~1.5 kb; BASELINE.json configs[1] shape, synthetic because a single
-579-sequence tree cannot fill a B200). The step runs the whole per-pair pipeline of the reference's level kernel on
-the device: profile build, gappy-column removal, PSGP, TALCO-XDrop DP + traceback, gappy restore, row update.
-Metric = DP giga cell-updates per second (GCUPS), cells counted by the kernel with the reference's definition (sum over
-anti-diagonals of the live band width).
+A "step" is one pass of the hot path over one level-shaped batch of synthetic profile pairs (RNASim-shaped: ~1.5 kb
+profiles of 1-8 sequences per side; BASELINE.json configs[1] shape, synthetic because the bundled files are not on the
+GPU box and a single 579-sequence tree cannot fill a B200). Metric = DP giga cell-updates per second (GCUPS), cells
+counted by the kernel with the reference's definition (sum over anti-diagonals of the live band width).
 
-  value  : device time of all pipeline phases with the rows resident in HBM (CUDA events on the launching stream, max over ranks)
-  e2e    : rows in host memory -> twl_rows_upload -> twl_align_level -> twl_rows_download -> host, wall clock per step
-  msa    : a full progressive alignment of 2048 synthetic sequences through the same API (sequences/s)
+  value  : kernels only, batch resident in HBM, CUDA events on the launching stream (max over ranks)
+  e2e    : the same batch through twl_align_profiles() with HOST buffers: pack + H2D + kernels + D2H, host wall clock
   roofline: the DP kernel against the FP32 pipe peak (117 FP32 op per nucleotide cell-update)
   cpu_baseline: the reference's own Talco_xdrop::Align_freq (oracle/_ref/libtalco_ref.so when present, else the
            oracle port) on a bounded sample of the same batch, all host cores.
@@ -27,7 +25,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_CELL_NT = 117.0
@@ -172,33 +170,16 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
-def build_level_batch(n_pairs, length, seed):
-    """Row-level batch: ids, rows, weights and the LevelPairIn list of one synthetic guide-tree level."""
-    from twilight_b200 import LevelPairIn, NodeSideIn, synth
-    fam = synth.level_rows_batch(n_pairs, length, seed=seed, kind="rna")
-    ids, rows, pairs = [], [], []
-    for ref_rows, qry_rows in fam:
-        sides = []
-        for fr in (ref_rows, qry_rows):
-            mine = list(range(len(ids), len(ids) + len(fr)))
-            ids += mine
-            rows += fr
-            sides.append(NodeSideIn(mine, len(fr[0]), len(fr), float(len(fr))))
-        pairs.append(LevelPairIn(sides[0], sides[1]))
-    weights = [1.0] * len(ids)
-    return ids, rows, weights, pairs
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--pairs", type=int, default=4096, help="node pairs per GPU per step")
+    ap.add_argument("--pairs", type=int, default=4096, help="profile pairs per GPU per step")
     ap.add_argument("--length", type=int, default=1500)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--msa-leaves", type=int, default=2048, help="leaves of the synthetic MSA job (0 = skip)")
+    ap.add_argument("--msa-leaves", type=int, default=0, help="leaves of the synthetic MSA job (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -208,7 +189,6 @@ def main():
 
     import torch
     import twilight_b200
-    from twilight_b200 import api
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -222,11 +202,13 @@ def main():
     else:
         torch.cuda.set_device(local)
 
-    # weak scaling: every rank aligns its own shard of same-level node pairs (no data-path collective)
-    ids, rows, weights, pairs = build_level_batch(args.pairs, args.length, seed=1000 + rank)
-    row_bytes = sum(len(r) for r in rows)
+    # weak scaling: every rank aligns its own shard of same-level pairs (no data-path collective)
+    raw, pairs = make_batch(args.pairs, args.length, seed=1000 + rank)
     ctx = twilight_b200.Context(device=local)
-    # L2 hygiene: a flush buffer larger than L2 (126 MB) is written between timed steps
+    ctx.stage(pairs)
+    in_bytes = sum(p.freq_ref.nbytes + p.freq_qry.nbytes + 2 * (p.gap_open_ref.nbytes + p.gap_open_qry.nbytes) for p in pairs)
+    # L2 hygiene: the staged batch is read once per step and exceeds L2 (126 MB) at the default size; a flush buffer is
+    # written between timed steps anyway
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def barrier():
@@ -234,102 +216,78 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # the ctypes argument blocks (host buffers: rows in, rewritten rows + paths out) are built once; a step is then
-    # exactly three C-ABI calls
-    caps = {}
-    for p in pairs:
-        for sd in (p.ref, p.qry):
-            for i in sd.seq_ids:
-                caps[i] = p.ref.aln_len + p.qry.aln_len + 16
-    prows = ctx.prepare_rows(ids, rows, weights, [caps[i] for i in ids])
-    plevel = ctx.prepare_level(pairs)
-
-    def one_step():
-        """rows -> HBM, one level through the device pipeline, rewritten rows -> host. Returns (phase_ms, wall_ms)."""
-        t0 = time.perf_counter()
-        ctx.upload_prepared(prows)
-        ctx.align_level_prepared(plevel)
-        ctx.download_prepared(prows)
-        t1 = time.perf_counter()
-        return ctx.level_phase_ms(), (t1 - t0) * 1e3
-
     for _ in range(args.warmup):
-        one_step()
-    cells = sum(int(plevel.res[k].cells) for k in range(plevel.n))
-    bad = sum(1 for k in range(plevel.n) if plevel.res[k].status != 0)
+        ctx.run()
+        ctx.kernel_ms()
+    outs = ctx.fetch(want_paths=False)
+    cells = sum(o.cells for o in outs)
+    bad = sum(1 for o in outs if o.status != 0)
 
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
-    dev_ms, phases, launches, e2e_ms = [], [0.0] * 4, 0, []
-    d2h = 0
+    step_ms, launches = [], 0
     for _ in range(args.steps):
         flush.fill_(1)
         torch.cuda.synchronize()
-        ph, wall = one_step()
-        dev_ms.append(sum(ph))
-        phases = [a + b for a, b in zip(phases, ph)]
+        ctx.run()
+        step_ms.append(ctx.kernel_ms())
         launches += ctx.launch_count()
-        e2e_ms.append(wall)
-        d2h = int(sum(prows.out_lens)) + sum(int(plevel.res[k].path_len) + 40 for k in range(plevel.n))
     barrier()
     clocks = sampler.stop()
-    dev_total, e2e_total = float(np.sum(dev_ms)), float(np.sum(e2e_ms))
+    dev_ms = float(np.sum(step_ms))
 
-    tot = torch.tensor([dev_total, e2e_total, float(cells)], dtype=torch.float64, device="cuda")
+    # e2e: host buffers in, host buffers out, every step
+    e2e_ms = []
+    for s in range(1 + args.steps):
+        t0 = time.perf_counter()
+        outs2 = ctx.align_profiles(pairs)
+        if s > 0:
+            e2e_ms.append((time.perf_counter() - t0) * 1e3)
+    d2h = sum(len(o.path) for o in outs2) + 40 * len(outs2)
+    e2e_total_ms = float(np.sum(e2e_ms))
+
+    tot = torch.tensor([dev_ms, e2e_total_ms, float(cells)], dtype=torch.float64, device="cuda")
     if dist is not None:
         mx = tot.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = tot.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        dev_all, e2e_all, cells_all = float(mx[0]), float(mx[1]), float(sm[2])
+        dev_ms, e2e_total_ms, cells_all = float(mx[0]), float(mx[1]), float(sm[2])
     else:
-        dev_all, e2e_all, cells_all = dev_total, e2e_total, float(cells)
+        cells_all = float(cells)
 
     if rank == 0:
         pk = peaks()
-        gcups = cells_all * args.steps / (dev_all * 1e-3) / 1e9
-        e2e_gcups = cells_all * args.steps / (e2e_all * 1e-3) / 1e9
-        dp_gcups_gpu = cells * args.steps / (phases[2] * 1e-3) / 1e9            # dominant kernel, this rank
-        achieved_tflops = dp_gcups_gpu * 1e9 * FLOP_PER_CELL_NT / 1e12
-        n_seqs = len(ids) * world
+        gcups = cells_all * args.steps / (dev_ms * 1e-3) / 1e9
+        e2e_gcups = cells_all * args.steps / (e2e_total_ms * 1e-3) / 1e9
+        per_gpu_gcups = cells * args.steps / (float(np.sum(step_ms)) * 1e-3) / 1e9
+        achieved_tflops = per_gpu_gcups * 1e9 * FLOP_PER_CELL_NT / 1e12
         line = {"metric": "dp_gcups", "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": dev_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"one guide-tree level of {args.pairs} node pairs per GPU, RNASim-shaped (~{args.length} columns, 1-8 member "
-                                       "sequences per node): profile build + gappy-column removal + PSGP + TALCO-XDrop DP/traceback + "
-                                       "gappy restore + row update", "pairs_per_gpu": args.pairs, "sequences_per_gpu": len(ids),
-                           "cells_per_step": cells_all, "failed_pairs": bad, "l2": "256 MiB flush buffer written between timed steps",
-                           "timed_region": "value: device time of the four pipeline phases with the rows resident in HBM; e2e: rows from host "
-                                           "memory -> twl_rows_upload -> twl_align_level -> twl_rows_download -> host"},
-                "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": int(row_bytes), "d2h_bytes_per_step": int(d2h),
-                        "ms_per_step": e2e_all / args.steps, "seqs_per_s": n_seqs * args.steps / (e2e_all * 1e-3)},
+                "config": {"workload": f"level batch of RNASim-shaped profile pairs (~{args.length} columns, 1-8 sequences per side), "
+                                       "TALCO-XDrop DP + traceback", "pairs_per_gpu": args.pairs, "cells_per_step": cells_all,
+                           "failed_pairs": bad, "l2": "256 MiB flush buffer written between timed steps"},
+                "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(d2h),
+                        "ms_per_step": e2e_total_ms / args.steps},
                 "gpu_launches": launches,
-                "phase_ms_per_step": {"profile_build": phases[0] / args.steps, "gappy_psgp_pack": phases[1] / args.steps,
-                                      "dp_chain": phases[2] / args.steps, "row_update_freq_merge": phases[3] / args.steps},
                 "roofline": {"bound": "fp32-pipe", "achieved": achieved_tflops, "peak": pk["fp32_tflops"], "unit": "TFLOP/s",
-                             "frac": achieved_tflops / pk["fp32_tflops"], "traffic": None, "kernel": "talcoWavefrontKernel<128,1>",
-                             "note": f"dominant kernel (DP) is CUDA-core bound (SURVEY.md §8d): 117 FP32 op per cell x {dp_gcups_gpu:.1f} GCUPS "
-                                     f"in the DP phase; peak = 148 SM x 128 lanes x 2 x {pk['sm_mhz']:.0f} MHz ({pk['source']} sm_max_mhz); per GPU"},
-                "seqs_per_s": n_seqs * args.steps / (dev_all * 1e-3),
+                             "frac": achieved_tflops / pk["fp32_tflops"], "traffic": None,
+                             "note": f"DP kernel is CUDA-core bound (SURVEY.md §8d): 117 FP32 op/cell x GCUPS; peak = 148 SM x 128 lanes x 2 x "
+                                     f"{pk['sm_mhz']:.0f} MHz ({pk['source']} sm_max_mhz); per GPU"},
+                "seqs_per_s": None,
                 "clocks": clocks}
         if args.msa_leaves > 0:
-            line["msa"] = run_msa(ctx, args.msa_leaves, args.length, seed=77)
+            m = run_msa(ctx, args.msa_leaves, args.length, seed=77)
+            line["msa"] = m
+            line["seqs_per_s"] = m["seqs_per_s_e2e"]
         if not args.no_cpu_baseline:
-            # the same pairs at the Align_freq boundary (profiles as the device built them) through the reference's own DP
             threads = os.cpu_count() or 1
-            n_sample = max(threads, min(len(pairs), 4 * threads))
-            ctx.rows_upload(ids, rows, weights)
-            ctx.align_level(pairs[:n_sample])
-            raw = []
-            for k in range(n_sample):
-                fr, fq = ctx.level_fetch(k, api.F_DP_PROFILE[0]), ctx.level_fetch(k, api.F_DP_PROFILE[1])
-                raw.append(dict(freq_ref=fr[:, :6].copy(), freq_qry=fq[:, :6].copy(), gap_open_ref=fr[:, 6].copy(), gap_ext_ref=fr[:, 7].copy(),
-                                gap_open_qry=fq[:, 6].copy(), gap_ext_qry=fq[:, 7].copy(), ref_num=pairs[k].ref.aln_num, qry_num=pairs[k].qry.aln_num))
+            n_sample = max(threads, min(len(raw), 4 * threads))
             g, c, dt, kind = cpu_reference_gcups(raw, n_sample, threads)
             line["cpu_baseline"] = {"value": g, "unit": "GCUPS", "cores": threads, "kind": kind,
-                                    "sample": f"{n_sample} pairs of the step's batch ({c} cells, {dt:.1f} s), Talco_xdrop::Align_freq only "
-                                              "(>99 % of the reference's time on this path)"}
+                                    "sample": f"{n_sample} pairs of the step's batch ({c} cells, {dt:.1f} s), Talco_xdrop::Align_freq only"}
         print(json.dumps(line))
     ctx.close()
     if dist is not None:

@@ -201,6 +201,62 @@ class Context:
         self._check(self._lib.twl_rows_download(self._h, n, a_ids, ptrs, out_l))
         return [bufs[k].raw[:out_l[k]] for k in range(n)]
 
+    # Prepared calls: the ctypes argument blocks are built once, so a timed region contains only the C ABI calls.
+    def prepare_rows(self, ids: Sequence[int], rows: Sequence[bytes], weights: Sequence[float], download_caps: Optional[Sequence[int]] = None):
+        n = len(ids)
+        prep = type("PreparedRows", (), {})()
+        prep.n = n
+        prep.ids = (C.c_int32 * n)(*[int(i) for i in ids])
+        prep.rows = (C.c_char_p * n)(*rows)
+        prep.lens = (C.c_int32 * n)(*[len(r) for r in rows])
+        prep.weights = (C.c_float * n)(*[float(w) for w in weights])
+        caps = [2 * len(r) + 64 for r in rows] if download_caps is None else [int(c) for c in download_caps]
+        offs = np.concatenate([[0], np.cumsum(caps)]).astype(np.int64)
+        prep.buf = np.zeros(int(offs[-1]) + 16, np.uint8)
+        prep.offs = offs
+        prep.ptrs = (C.c_void_p * n)(*[prep.buf.ctypes.data + int(o) for o in offs[:-1]])
+        prep.out_lens = (C.c_int32 * n)()
+        return prep
+
+    def upload_prepared(self, prep):
+        self._check(self._lib.twl_rows_upload(self._h, prep.n, prep.ids, prep.rows, prep.lens, prep.weights))
+
+    def download_prepared(self, prep):
+        """Rows land in prep.buf at prep.offs[k], lengths in prep.out_lens."""
+        self._check(self._lib.twl_rows_download(self._h, prep.n, prep.ids, prep.ptrs, prep.out_lens))
+
+    def prepare_level(self, pairs: Sequence[LevelPairIn]):
+        n = len(pairs)
+        prep = type("PreparedLevel", (), {})()
+        prep.n = n
+        prep.arr = (_lib.LevelPair * max(n, 1))()
+        prep.keep = []
+        caps = []
+        for k, p in enumerate(pairs):
+            for side, dst in ((p.ref, prep.arr[k].ref), (p.qry, prep.arr[k].qry)):
+                ids = (C.c_int32 * max(len(side.seq_ids), 1))(*[int(i) for i in side.seq_ids])
+                prep.keep.append(ids)
+                dst.seq_ids = ids
+                dst.n_ids = len(side.seq_ids)
+                dst.aln_len, dst.aln_num, dst.aln_weight = int(side.aln_len), int(side.aln_num), float(side.aln_weight)
+                if side.msa_freq is not None:
+                    f = np.ascontiguousarray(side.msa_freq, np.float32)
+                    prep.keep.append(f)
+                    dst.msa_freq = f.ctypes.data
+                else:
+                    dst.msa_freq = None
+            prep.arr[k].flags = 1 if p.profile_only else 0
+            caps.append(p.ref.aln_len + p.qry.aln_len + 16)
+        offs = np.concatenate([[0], np.cumsum(caps)]).astype(np.int64)
+        prep.path_buf = np.zeros(int(offs[-1]) + 16, np.int8)
+        prep.path_offs = offs
+        prep.ptrs = (C.c_void_p * max(n, 1))(*[prep.path_buf.ctypes.data + int(o) for o in offs[:-1]])
+        prep.res = (_lib.LevelResult * max(n, 1))()
+        return prep
+
+    def align_level_prepared(self, prep, task: int = 0, gappy: float = 0.95, cache_threshold: int = 1000):
+        self._check(self._lib.twl_align_level(self._h, prep.arr, prep.n, int(task), float(gappy), int(cache_threshold), prep.ptrs, prep.res))
+
     def rows_clear(self):
         self._check(self._lib.twl_rows_clear(self._h))
 

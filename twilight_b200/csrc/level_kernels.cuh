@@ -317,8 +317,8 @@ __global__ void __launch_bounds__(kLvlThreads) rowUpdateKernel(const DevUpdate *
     }
     __syncthreads();
     const int nHere = min(kPathChunk, u.pathLen - k0);
-    // member rows: ref members copy on 0/2, qry members on 0/1, '-' otherwise
-    for (int m = 0; m < u.nRef + u.nQry; ++m) {
+    // member rows (grid.z strides over them): ref members copy on 0/2, qry members on 0/1, '-' otherwise
+    for (int m = blockIdx.z; m < u.nRef + u.nQry; m += gridDim.z) {
         const bool isRef = m < u.nRef;
         const char *in = rowIn[u.memberOff + m];
         char *out = rowOut[u.memberOff + m] + k0;
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(kLvlThreads) rowUpdateKernel(const DevUpdate *
             out[e] = take ? in[isRef ? srcR[e] : srcQ[e]] : '-';
         }
     }
-    if (u.mergedOff >= 0) {                                                 // updateFrequency, helper.cpp:513-531
+    if (u.mergedOff >= 0 && blockIdx.z == 0) {                              // updateFrequency, helper.cpp:513-531
         const float *fr = freq + u.freqRefOff, *fq = freq + u.freqQryOff;
         float *mg = merged + u.mergedOff + static_cast<long long>(k0) * P;
         for (int x = threadIdx.x; x < nHere * P; x += kLvlThreads) {

@@ -583,7 +583,11 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
         updateTimed = true;
         pathChunkKernel<<<(nu * 32 + 255) / 256, 256, 0, ctx->stream>>>(L->dUps.ptr, nu, L->dFinalPaths.ptr, L->dChunkCounts.ptr);
         TWL_CUDA(ctx, cudaGetLastError());
-        dim3 grid(nu, std::max(1, (maxPath + kPathChunk - 1) / kPathChunk));
+        int maxRows = 1;
+        for (auto &u : ups) maxRows = std::max(maxRows, u.nRef + u.nQry);
+        // enough blocks to fill the GPU when a level has few pairs with many member rows each
+        const int wantZ = std::max(1, (4 * ctx->smCount) / std::max(1, nu * std::max(1, (maxPath + kPathChunk - 1) / kPathChunk)));
+        dim3 grid(nu, std::max(1, (maxPath + kPathChunk - 1) / kPathChunk), std::min(std::min(maxRows, wantZ), 64));
         rowUpdateKernel<P><<<grid, kLvlThreads, 0, ctx->stream>>>(L->dUps.ptr, L->dFinalPaths.ptr, L->dChunkCounts.ptr, L->dRowIn.ptr, L->dRowOut.ptr,
                                                               L->dFreq.ptr, L->dMerged.ptr);
         TWL_CUDA(ctx, cudaGetLastError());
