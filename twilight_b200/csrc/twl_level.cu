@@ -46,6 +46,10 @@ struct TwlLevelState {
     DevBuf<twl::DevUpdate> dUps;
     DevBuf<int8_t> dFinalPaths;
     DevBuf<signed char> dAaLut;
+    PinBuf<twl::DevResult> hRes;
+    PinBuf<int8_t> hPathsWo;
+    PinBuf<int32_t> hRunsPin;
+    PinBuf<char> hConsPin;
     DevBuf<twl::RowCopy> dCopies;
     DevBuf<char> dStage;
     PinBuf<char> hStage;
@@ -169,6 +173,7 @@ void twlLevelDestroy(twl_ctx *ctx) {
     L->dSides.release(); L->dRowIn.release(); L->dRowOut.release(); L->dRowW.release(); L->dRaw.release(); L->dFreq.release();
     L->dMerged.release(); L->dCons.release(); L->dRuns.release(); L->dChunkCounts.release(); L->dUps.release();
     L->dFinalPaths.release(); L->dAaLut.release(); L->dCopies.release(); L->dStage.release(); L->hStage.release();
+    L->hRes.release(); L->hPathsWo.release(); L->hRunsPin.release(); L->hConsPin.release();
     for (auto &e : L->ev) if (e) cudaEventDestroy(e);
     delete L;
     ctx->level = nullptr;
@@ -384,6 +389,20 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
     TWL_CUDA(ctx, cudaMemcpyAsync(ctx->dPairs.ptr, dp.data(), sizeof(DevPair) * n, cudaMemcpyHostToDevice, ctx->stream));
     TWL_CUDA(ctx, cudaMemcpyAsync(ctx->dOrder.ptr, order.data(), sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
 
+    // host-side result buffers are sized before anything is enqueued so the device never waits on the host between phases
+    std::vector<int> work;
+    for (int x : order) if (!(pairs[begin + x].flags & TWL_PAIR_PROFILE_ONLY)) work.push_back(x);
+    TWL_CUDA(ctx, L->hRes.reserve(n));
+    TWL_CUDA(ctx, L->hPathsWo.reserve(std::max<size_t>(pathBytes, 16)));
+    TWL_CUDA(ctx, L->hRunsPin.reserve(std::max<size_t>(runInts, 2)));
+    TWL_CUDA(ctx, L->hConsPin.reserve(std::max<size_t>(consBytes, 16)));
+    DevResult *res = L->hRes.ptr;
+    for (int p = 0; p < n; ++p) { res[p].status = 0; res[p].pathLen = 0; res[p].tiles = 0; res[p].pad = 0; res[p].cells = 0; res[p].diagonals = 0; }
+    int8_t *hostPaths = L->hPathsWo.ptr;
+    int32_t *hRuns = L->hRunsPin.ptr;
+    char *hCons = L->hConsPin.ptr;
+    std::vector<std::vector<int8_t>> finalPath(n);
+
     // ---- phase 1: profiles + consensus (+ msaFreq cache); phase 2: gappy-column compaction + PSGP + DP packing
     TWL_CUDA(ctx, cudaEventRecord(L->ev[0], ctx->stream));
     {
@@ -399,15 +418,7 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
     TWL_CUDA(ctx, cudaEventRecord(L->ev[2], ctx->stream));
     ctx->lastLaunches += 2;
 
-    // ---- phase 3: DP chain (pairs flagged profile-only are parked with an impossible work order: they are simply not listed)
-    std::vector<int> work;
-    for (int x : order) if (!(pairs[begin + x].flags & TWL_PAIR_PROFILE_ONLY)) work.push_back(x);
-    std::vector<DevResult> res(n);
-    for (auto &r : res) { r.status = 0; r.pathLen = 0; r.tiles = 0; r.pad = 0; r.cells = 0; r.diagonals = 0; }
-    std::vector<int8_t> hostPaths(std::max<size_t>(pathBytes, 1));
-    std::vector<std::vector<int8_t>> finalPath(n);
-    std::vector<int32_t> hRuns(std::max<size_t>(runInts, 2));
-    std::vector<char> hCons(std::max<size_t>(consBytes, 1));
+    // ---- phase 3: DP chain (pairs flagged profile-only are simply not listed)
     bool first = true;
     while (!work.empty()) {
         const int nw = static_cast<int>(work.size());
@@ -415,12 +426,12 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
         int rc = twlLaunchDpChain(ctx, nw, maxF);
         if (rc != TWL_OK) return rc;
         if (first) TWL_CUDA(ctx, cudaEventRecord(L->ev[3], ctx->stream));
-        TWL_CUDA(ctx, cudaMemcpyAsync(res.data(), ctx->dResults.ptr, sizeof(DevResult) * n, cudaMemcpyDeviceToHost, ctx->stream));
-        TWL_CUDA(ctx, cudaMemcpyAsync(hostPaths.data(), ctx->dPaths.ptr, pathBytes, cudaMemcpyDeviceToHost, ctx->stream));
+        TWL_CUDA(ctx, cudaMemcpyAsync(res, ctx->dResults.ptr, sizeof(DevResult) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        TWL_CUDA(ctx, cudaMemcpyAsync(hostPaths, ctx->dPaths.ptr, pathBytes, cudaMemcpyDeviceToHost, ctx->stream));
         if (first) {
             TWL_CUDA(ctx, cudaMemcpyAsync(sides.data(), L->dSides.ptr, sizeof(DevSide) * nSides, cudaMemcpyDeviceToHost, ctx->stream));
-            TWL_CUDA(ctx, cudaMemcpyAsync(hRuns.data(), L->dRuns.ptr, sizeof(int32_t) * runInts, cudaMemcpyDeviceToHost, ctx->stream));
-            TWL_CUDA(ctx, cudaMemcpyAsync(hCons.data(), L->dCons.ptr, consBytes, cudaMemcpyDeviceToHost, ctx->stream));
+            TWL_CUDA(ctx, cudaMemcpyAsync(hRuns, L->dRuns.ptr, sizeof(int32_t) * runInts, cudaMemcpyDeviceToHost, ctx->stream));
+            TWL_CUDA(ctx, cudaMemcpyAsync(hCons, L->dCons.ptr, consBytes, cudaMemcpyDeviceToHost, ctx->stream));
             TWL_CUDA(ctx, cudaMemcpyAsync(dp.data(), ctx->dPairs.ptr, sizeof(DevPair) * n, cudaMemcpyDeviceToHost, ctx->stream));
         }
         TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -435,7 +446,7 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
                 if (dp[x].refLen < 1) wo.assign(std::max(dp[x].qryLen, 0), 1);
                 else wo.assign(std::max(dp[x].refLen, 0), 2);
                 r.pathLen = static_cast<int>(wo.size());
-                std::memcpy(hostPaths.data() + dp[x].alnOff, wo.data(), wo.size());
+                std::memcpy(hostPaths + dp[x].alnOff, wo.data(), wo.size());
             }
             if (r.status != 0 && task != 0) {     // retry ladder, alignment-cpu.cpp:116-129
                 if (r.status == 3) continue;
@@ -452,8 +463,8 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
     if (first) {   // nothing to align in this chunk: still need the side outputs
         TWL_CUDA(ctx, cudaEventRecord(L->ev[3], ctx->stream));
         TWL_CUDA(ctx, cudaMemcpyAsync(sides.data(), L->dSides.ptr, sizeof(DevSide) * nSides, cudaMemcpyDeviceToHost, ctx->stream));
-        TWL_CUDA(ctx, cudaMemcpyAsync(hRuns.data(), L->dRuns.ptr, sizeof(int32_t) * runInts, cudaMemcpyDeviceToHost, ctx->stream));
-        TWL_CUDA(ctx, cudaMemcpyAsync(hCons.data(), L->dCons.ptr, consBytes, cudaMemcpyDeviceToHost, ctx->stream));
+        TWL_CUDA(ctx, cudaMemcpyAsync(hRuns, L->dRuns.ptr, sizeof(int32_t) * runInts, cudaMemcpyDeviceToHost, ctx->stream));
+        TWL_CUDA(ctx, cudaMemcpyAsync(hCons, L->dCons.ptr, consBytes, cudaMemcpyDeviceToHost, ctx->stream));
         TWL_CUDA(ctx, cudaMemcpyAsync(dp.data(), ctx->dPairs.ptr, sizeof(DevPair) * n, cudaMemcpyDeviceToHost, ctx->stream));
         TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
@@ -471,15 +482,15 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
                 for (int s = 0; s < 2; ++s) {
                     const DevSide &d = sides[2 * p + s];
                     kp.newLen[s] = d.newLen; kp.nRuns[s] = d.nRuns;
-                    kp.runs[s].assign(hRuns.begin() + d.runsOff, hRuns.begin() + d.runsOff + 2 * d.nRuns);
-                    kp.cons[s].assign(hCons.begin() + d.consOff, hCons.begin() + d.consOff + d.alnLen);
+                    kp.runs[s].assign(hRuns + d.runsOff, hRuns + d.runsOff + 2 * d.nRuns);
+                    kp.cons[s].assign(hCons + d.consOff, hCons + d.consOff + d.alnLen);
                 }
                 out.status = res[p].status; out.tiles = res[p].tiles; out.cells = res[p].cells; out.diagonals = res[p].diagonals;
                 out.ref_len_dp = sr.newLen; out.qry_len_dp = sq.newLen; out.path_len = 0;
                 out.cached = (sr.freqOutOff >= 0 ? 1 : 0) | (sq.freqOutOff >= 0 ? 2 : 0);
                 if (in.flags & TWL_PAIR_PROFILE_ONLY) { out.status = 0; continue; }
                 if (out.status != 0) continue;
-                kp.pathWo.assign(hostPaths.begin() + dp[p].alnOff, hostPaths.begin() + dp[p].alnOff + res[p].pathLen);
+                kp.pathWo.assign(hostPaths + dp[p].alnOff, hostPaths + dp[p].alnOff + res[p].pathLen);
                 kp.pathWoLen = res[p].pathLen;
                 std::vector<int8_t> &fp = finalPath[p];
                 fp.clear();
