@@ -313,6 +313,15 @@ def main():
                                      f"in the DP phase; peak = 148 SM x 128 lanes x 2 x {pk['sm_mhz']:.0f} MHz ({pk['source']} sm_max_mhz); per GPU"},
                 "seqs_per_s": n_seqs * args.steps / (dev_all * 1e-3),
                 "clocks": clocks}
+        # the HBM-bound kernels of the step against the measured copy bandwidth (algorithmic bytes)
+        P = 6
+        prof_bytes = row_bytes + sum((p.ref.aln_len + p.qry.aln_len) * P * 4 for p in pairs)
+        new_len = {k: int(plevel.res[k].path_len) for k in range(plevel.n)}
+        upd_bytes = sum(p.ref.aln_num * (p.ref.aln_len + new_len[k]) + p.qry.aln_num * (p.qry.aln_len + new_len[k]) + new_len[k] for k, p in enumerate(pairs))
+        pack_bytes = sum((p.ref.aln_len + p.qry.aln_len) * (P * 4 + (P + 2) * 4) for p in pairs)
+        line["hbm_kernels"] = {
+            name: {"bytes_per_step": int(b), "GB/s": b / (ms / args.steps) / 1e6, "frac_of_measured_copy": b / (ms / args.steps) / 1e6 / pk["hbm_gbs"]}
+            for name, b, ms in (("profile_build", prof_bytes, phases[0]), ("gappy_psgp_pack", pack_bytes, phases[1]), ("row_update", upd_bytes, phases[3]))}
         if args.msa_leaves > 0:
             line["msa"] = run_msa(ctx, args.msa_leaves, args.length, seed=77)
         if not args.no_cpu_baseline:

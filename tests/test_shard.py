@@ -1,0 +1,75 @@
+"""Host-side sharding logic (CPU): LPT partition, subtree affinity, and a world_size-2 gloo run in which every rank
+aligns its own shard of a level (with the CPU oracle standing in for the device) and rank 0 gathers the results."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_lpt_partition_balances_and_covers():
+    from twilight_b200 import shard
+    rng = np.random.default_rng(0)
+    costs = rng.integers(1000, 9000, 257).astype(float)
+    parts = shard.lpt_partition(costs, 8)
+    assert sorted(i for p in parts for i in p) == list(range(257))
+    loads = [costs[p].sum() for p in parts]
+    assert max(loads) - min(loads) <= costs.max()
+
+
+def test_subtree_affinity_keeps_subtrees_together():
+    from twilight_b200 import shard, synth
+    tree = synth.random_tree(200, seed=3)
+    levels = synth.levels_bottom_up(tree)
+    owner = shard.subtree_affinity(levels, 8, tree.n_nodes)
+    assert owner.min() >= 0 and owner.max() <= 7
+    counts = np.bincount(owner[:200], minlength=8)
+    assert counts.min() > 0 and counts.max() <= 3 * 200 // 8
+    moves = sum(1 for lv in levels for a, b, p in lv if owner[a] != owner[b])
+    assert moves <= 7          # rows cross ranks only at the (world-1) joins at the top of the tree
+
+
+def _worker(rank, world, port, out_path):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from tests import oracle_lib as ol
+    from twilight_b200 import shard, synth
+    raw = synth.profile_pair_batch(10, 300, seed=5)
+    costs = [p["freq_ref"].shape[0] + p["freq_qry"].shape[0] for p in raw]
+    mine = shard.lpt_partition(costs, world)[rank]
+    cfg = ol.TalcoCfg()
+    res = {}
+    for i in mine:
+        p = raw[i]
+        path, err, cells, tiles, _ = ol.port_talco(cfg, p["freq_ref"], p["freq_qry"], p["gap_open_ref"], p["gap_ext_ref"], p["gap_open_qry"],
+                                                   p["gap_ext_qry"], p["ref_num"], p["qry_num"])
+        res[i] = (path.tobytes(), err, cells)
+    slowest = shard.allreduce_max(float(len(mine)), dist)
+    got = shard.gather_objects(res, dist, dst=0)
+    if rank == 0:
+        merged = {}
+        for part in got:
+            merged.update(part)
+        np.save(out_path, np.array([len(merged), int(slowest), sum(v[2] for v in merged.values())]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_level_shard(tmp_path):
+    import torch.multiprocessing as mp
+    from tests import oracle_lib as ol
+    from twilight_b200 import synth
+    out = str(tmp_path / "res.npy")
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    n, slowest, cells = np.load(out)
+    raw = synth.profile_pair_batch(10, 300, seed=5)
+    cfg = ol.TalcoCfg()
+    want = sum(ol.port_talco(cfg, p["freq_ref"], p["freq_qry"], p["gap_open_ref"], p["gap_ext_ref"], p["gap_open_qry"], p["gap_ext_qry"],
+                             p["ref_num"], p["qry_num"])[2] for p in raw)
+    assert n == 10 and slowest == 5 and cells == want
