@@ -201,3 +201,44 @@ def ref_pipeline(type_, cfg, ref_state, qry_state, gappy=0.95, current_task=0):
     raw = out["new_rows"].raw
     res["new_rows"] = [raw[k * cap:k * cap + new_len.value] for k in range(nR + nQ)] if n_w.value else []
     return res
+
+
+_B62_NCBI_ORDER = "ARNDCQEGHILKMFPSTWYV"
+_B62_NCBI = """
+ 4 -1 -2 -2  0 -1 -1  0 -2 -1 -1 -1 -1 -2 -1  1  0 -3 -2  0
+-1  5  0 -2 -3  1  0 -2  0 -3 -2  2 -1 -3 -2 -1 -1 -3 -2 -3
+-2  0  6  1 -3  0  0  0  1 -3 -3  0 -2 -3 -2  1  0 -4 -2 -3
+-2 -2  1  6 -3  0  2 -1 -1 -3 -4 -1 -3 -3 -1  0 -1 -4 -3 -3
+ 0 -3 -3 -3  9 -3 -4 -3 -3 -1 -1 -3 -1 -2 -3 -1 -1 -2 -2 -1
+-1  1  0  0 -3  5  2 -2  0 -3 -2  1  0 -3 -1  0 -1 -2 -1 -2
+-1  0  0  2 -4  2  5 -2  0 -3 -3  1 -2 -3 -1  0 -1 -3 -2 -2
+ 0 -2  0 -1 -3 -2 -2  6 -2 -4 -4 -2 -3 -3 -2  0 -2 -2 -3 -3
+-2  0  1 -1 -3  0  0 -2  8 -3 -3 -1 -2 -1 -2 -1 -2 -2  2 -3
+-1 -3 -3 -3 -1 -3 -3 -4 -3  4  2 -3  1  0 -3 -2 -1 -3 -1  3
+-1 -2 -3 -4 -1 -2 -3 -4 -3  2  4 -2  2  0 -3 -2 -1 -2 -1  1
+-1  2  0 -1 -3  1  1 -2 -1 -3 -2  5 -1 -3 -1  0 -1 -3 -2 -2
+-1 -1 -2 -3 -1  0 -2 -3 -2  1  2 -1  5  0 -2 -1 -1 -1 -1  1
+-2 -3 -3 -3 -2 -3 -3 -3 -1  0  0 -3  0  6 -4 -2 -2  1  3 -1
+-1 -2 -2 -1 -3 -1 -1 -2 -2 -3 -3 -1 -2 -4  7 -1 -1 -4 -3 -2
+ 1 -1  1  0 -1  0  0  0 -1 -2 -2  0 -1 -2 -1  4  1 -3 -2 -2
+ 0 -1  0 -1 -1 -1 -1 -2 -2 -1 -1 -1 -1 -2 -1  1  5 -2 -2  0
+-3 -3 -4 -4 -2 -2 -3 -2 -2 -3 -2 -3 -1  1 -4 -3 -2 11  2 -3
+-2 -2 -2 -3 -2 -1 -2 -3  2 -1 -1 -2 -1  3 -3 -2 -2  2  7 -1
+ 0 -3 -3 -3 -1 -2 -2 -3 -3  3  1 -2  1 -1 -2 -2  0 -3 -1  4
+"""
+
+
+def protein_matrix(scale=5.0, wildcard=False):
+    """21x21 protein matrix in TWILIGHT's layout (ACDEFGHIKLMNPQRSTVWY + X): scale x BLOSUM62, X row/column 0
+    (scoring-matrix.cpp:113-137). The BLOSUM values here are the public NCBI table; the matrix is an INPUT to both the
+    oracle and the device, so parity does not depend on them."""
+    raw = np.array([[float(v) for v in line.split()] for line in _B62_NCBI.strip().splitlines()], np.float32)
+    order = "ACDEFGHIKLMNPQRSTVWY"
+    idx = [_B62_NCBI_ORDER.index(c) for c in order]
+    m = np.zeros((21, 21), np.float32)
+    m[:20, :20] = scale * raw[np.ix_(idx, idx)]
+    if wildcard:
+        n = scale * float(np.mean(np.diag(raw)))
+        m[20, :] = n
+        m[:, 20] = n
+    return m
