@@ -47,7 +47,7 @@ __device__ __forceinline__ float orderedFloat(int o) { return __int_as_float(o ^
 __device__ __forceinline__ void prefetchL1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // Split-phase CTA barrier on an mbarrier object in shared memory: arrive (release) now, wait (acquire) later, so that
-// independent work can be issued in between. Every thread of the CTA arrives exactly once per phase.
+// independent work can be issued in between. One elected lane per warp arrives (after __syncwarp) once per phase.
 __device__ __forceinline__ void mbarInit(unsigned addr, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
 }
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned mbarAddr = static_cast<unsigned>(__cvta_generic_to_shared(&sMbar));
     unsigned mbarPhase = 0;
-    if (tid == 0) mbarInit(mbarAddr, NT);
+    if (tid == 0) mbarInit(mbarAddr, NW);   // one elected lane per warp arrives
     __syncthreads();
     uint8_t *tb = a.tbScratch + static_cast<size_t>(blockIdx.x) * a.tbStride;   // tb[k][rho], row stride W
     const int marker = a.marker;
@@ -428,11 +428,12 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
                 const unsigned wBad = __reduce_or_sync(0xffffffffu, pendBad);
                 if (lane == 31) edgeOut[g0 * 8] = make_float2(h1[kSlots - 1], i1[kSlots - 1]);
                 if (lane == 0) redOut[g0 * 8] = make_int4(wMax, wLo, wHi, static_cast<int>(wBad));
-                mbarArrive(mbarAddr);
+                __syncwarp();                                           // the warp's shared-memory writes happen-before lane 0's release
+                if (lane == 0) mbarArrive(mbarAddr);
 
                 // while the other warps catch up: scores of diagonal k+1 for the rows this thread holds now (the band of
                 // k+1 lies inside [L0, U0+1]; if the thread is re-assigned meanwhile the scores are recomputed)
-                if (k + 1 < nDiag && __any_sync(0xffffffffu, (iBase <= U0 + 1) && (iBase + kSlots - 1 >= L0))) {
+                if (a.overlap && k + 1 < nDiag && __any_sync(0xffffffffu, (iBase <= U0 + 1) && (iBase + kSlots - 1 >= L0))) {
                     scorePhase(k + 1, iBase);
                     specBase = iBase;
                 }
