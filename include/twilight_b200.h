@@ -165,8 +165,7 @@ float twl_last_kernel_ms(const twl_ctx *ctx);
 int twl_last_launch_count(const twl_ctx *ctx);
 
 /* Tuning / diagnostics switches. "force_generic" = 1 routes nucleotide batches through the wide-band generic kernel
- * instead of the register-resident wavefront kernel (results are identical; used by the A/B parity tests).
- * "overlap" = -1 (auto) / 0 / 1: compute the next anti-diagonal's scores while the per-diagonal barrier completes. */
+ * instead of the register-resident wavefront kernel (results are identical; used by the A/B parity tests). */
 int twl_set_option(twl_ctx *ctx, const char *name, int value);
 
 /* Device self-test: evaluates the reciprocal-based exact division used by the DP kernels and the IEEE divide on n

@@ -46,26 +46,6 @@ __device__ __forceinline__ float orderedFloat(int o) { return __int_as_float(o ^
 
 __device__ __forceinline__ void prefetchL1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-// Split-phase CTA barrier on an mbarrier object in shared memory: arrive (release) now, wait (acquire) later, so that
-// independent work can be issued in between. One elected lane per warp arrives (after __syncwarp) once per phase.
-__device__ __forceinline__ void mbarInit(unsigned addr, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbarArrive(unsigned addr) {
-    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(addr) : "memory");
-}
-__device__ __forceinline__ void mbarWait(unsigned addr, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}" ::"r"(addr), "r"(parity) : "memory");
-}
-
 // Column-pair numerators of the four slots of a thread. MC = 0: any 5x5 matrix, full reference order.
 // MC = 1 ("DNA3Z"): the built-in nucleotide matrix shape (scoring-matrix.cpp:103-112 without --wildcard):
 // S[l][l] = A, S[l][m] = B for |l-m| = 2, C otherwise, and an all-zero N row/column. The N terms of the reference sum
@@ -112,13 +92,8 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
     constexpr int CW = W + 4;                       // convergence arrays, reference indexing (row - L[k]) plus padding
     __shared__ WaveShared sh;
     __shared__ int sCS[3][CW], sCI[2][CW], sCD[2][CW];
-    __shared__ __align__(8) unsigned long long sMbar;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned mbarAddr = static_cast<unsigned>(__cvta_generic_to_shared(&sMbar));
-    unsigned mbarPhase = 0;
-    if (tid == 0) mbarInit(mbarAddr, NW);   // one elected lane per warp arrives
-    __syncthreads();
     uint8_t *tb = a.tbScratch + static_cast<size_t>(blockIdx.x) * a.tbStride;   // tb[k][rho], row stride W
     const int marker = a.marker;
     const int rho0 = tid * kSlots;
@@ -190,98 +165,16 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
             float2 *const edgeOut = &sh.edge[0][warp];
             int4 *const redOut = &sh.red[0][warp];
 
-            // Scores of the thread's four rows on diagonal kk: reference columns kk - (base + c) -> num[], plus the
-            // reference-side gap penalties. Depends only on the profiles, never on the DP state, which is why it can be
-            // evaluated for diagonal k+1 while the reduction of diagonal k is still in flight.
-            float num[kSlots], gOpR[kSlots], gExR[kSlots];
-            int specBase = -2;                                          // rows the current num[] was computed for (-2: none)
-            auto scorePhase = [&](int kk, int base) {
-                float r[kSlots][6];
-                bool gapQ = false, gapR = false;
-                // Slot c reads global reference column m-c with m = refOff + kk - base. base is a multiple of 4, so m&3 is
-                // the same for every thread: the four slots hit the four streams of the de-interleaved layout at float4
-                // index m>>2 (or one less once m-c crosses a multiple of 4). Columns outside [0, refLen) are only touched
-                // by slots that are not live; the profile buffer is padded so the reads stay inside the allocation and
-                // their values are discarded.
-                const int m = refOff + kk - base;
-                const int u = (refOff + kk) & 3;
-                const float4 *pX = refX + (m >> 2);
-                const long long yOff = 4 * static_cast<long long>(pr.refN4);
-#pragma unroll
-                for (int c = 0; c < kSlots; ++c) {
-                    const int stream = (u - c) & 3;
-                    const int at = stream * pr.refN4 - ((c > u) ? 1 : 0);
-                    const float4 x = __ldg(pX + at);
-                    const float4 y = __ldg(pX + at + yOff);
-                    r[c][0] = x.x; r[c][1] = x.y; r[c][2] = x.z; r[c][3] = x.w; r[c][4] = y.x; r[c][5] = y.y;
-                    gOpR[c] = y.z; gExR[c] = y.w;
-                    gapR = gapR || (y.y != 0.0f);
-                    gapQ = gapQ || (q[c][5] != 0.0f);
-                }
-                numerators4<MC>(r, q, a, num);
-                // gap-character terms (TALCO-XDrop.cpp:393-394): each loop adds exact zeros unless the query (resp.
-                // reference) column holds gaps, so it is skipped when no lane of the warp needs it
-                if (__any_sync(0xffffffffu, gapQ)) {
-#pragma unroll
-                    for (int c = 0; c < kSlots; ++c)
-#pragma unroll
-                        for (int l = 0; l < 5; ++l) num[c] = __fmaf_rn(__fmul_rn(r[c][l], q[c][5]), gapChar, num[c]);
-                }
-                if (__any_sync(0xffffffffu, gapR)) {
-#pragma unroll
-                    for (int c = 0; c < kSlots; ++c)
-#pragma unroll
-                        for (int mm = 0; mm < 5; ++mm) num[c] = __fmaf_rn(__fmul_rn(r[c][5], q[c][mm]), gapChar, num[c]);
-                }
-                if (divMode == 1) {
-                    // reciprocal-based exact division; numerators that are non-zero but tiny (|n| < 2^-60, where the
-                    // quotient or the FMA residual could leave the normal range) take the IEEE divide instead
-                    unsigned tiny = 0xffffffffu;
-#pragma unroll
-                    for (int c = 0; c < kSlots; ++c) tiny = min(tiny, (__float_as_uint(num[c]) & 0x7fffffffu) - 1u);
-                    if (tiny < 0x21800000u - 1u) {
-#pragma unroll
-                        for (int c = 0; c < kSlots; ++c) num[c] = __fdiv_rn(num[c], denom);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < kSlots; ++c) num[c] = exactDivNormal(num[c], denom, rcp);
-                    }
-                } else if (divMode == 2) {
-#pragma unroll
-                    for (int c = 0; c < kSlots; ++c) num[c] = __fdiv_rn(num[c], denom);
-                }
-            };
-
-            // convergence test of the previous diagonal, resolved one diagonal late (its all-equal bits travel with the
-            // next reduction, so a diagonal costs a single barrier)
-            bool pend = false;
-            int pendI = 0, pendD = 0, pendS = 0;
-            unsigned pendBad = 0;
-            float pendMaxPrime = 0.0f;
-            unsigned lastWidth = 0;
-
             for (int k = 0; k < nDiag; ++k) {
                 g0 ^= 1;
                 const int g1 = g0 ^ 1;
                 const int width = U0 - L0 + 1;
                 const int Lb = L0 & ~(kSlots - 1);                     // window base: multiple of 4 so a thread's rows never wrap
                 if (width <= 0 || width > cap || U0 - Lb >= W) {       // :323-338, plus this kernel's own capacity
-                    if (pend) {
-                        // a convergence test is still open: if it ends the tile on diagonal k-1 (:609) the reference never
-                        // reaches this diagonal. One block vote settles it (rare path).
-                        const int badID = __syncthreads_or((pendBad & 1u) != 0);
-                        const int badS = __syncthreads_or((pendBad & 2u) != 0);
-                        const int cS = badS ? -1 : pendS;
-                        if (!badID && pendI == pendD && pendI == cS && prevConvS == cS && pendI != -1 && pendMaxPrime < 0.0f) {
-                            converged = true; convValue = prevConvS; convScore = pendMaxPrime; stopped = true;
-                            break;
-                        }
-                    }
                     error = (width <= 0) ? 1 : ((width > cap) ? 2 : kStatusRetryWide);
                     break;
                 }
                 tileCells += static_cast<unsigned>(width);
-                lastWidth = static_cast<unsigned>(width);
                 const float pruneBelow = __fsub_rn(maxScore, xdropF);
 
                 if (tid == 0) {   // warm L1 for the lines the band edges will touch a few diagonals from now
@@ -319,14 +212,64 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
                 int myLo = 0x7fffffff, myHi = -0x7fffffff;
                 unsigned tbWord = 0, actBits = 0;
                 const bool anyAct = (iBase <= U0) && (iBase + kSlots - 1 >= L0);
-                int cs[kSlots], ci[kSlots], cd[kSlots];
-#pragma unroll
-                for (int c = 0; c < kSlots; ++c) cs[c] = ci[c] = cd[c] = 0;
 
                 if (__any_sync(0xffffffffu, anyAct)) {
-                    // scores: normally already computed during the previous diagonal's barrier wait
-                    if (__any_sync(0xffffffffu, anyAct && specBase != iBase)) scorePhase(k, iBase);
-                    specBase = -2;
+                    float r[kSlots][6], gOpR[kSlots], gExR[kSlots], num[kSlots];
+                    bool gapQ = false, gapR = false;
+                    {
+                        // Slot c reads global reference column m-c with m = refOff + k - iBase. iBase is a multiple of 4,
+                        // so m&3 is the same for every thread: the four slots hit the four streams of the de-interleaved
+                        // layout at float4 index m>>2 (or one less once m-c crosses a multiple of 4). Columns outside
+                        // [0, refLen) are only touched by slots that are not live; the profile buffer is padded so the
+                        // reads stay inside the allocation and their values are discarded.
+                        const int m = refOff + k - iBase;
+                        const int u = (refOff + k) & 3;
+                        const float4 *pX = refX + (m >> 2);
+                        const long long yOff = 4 * static_cast<long long>(pr.refN4);
+#pragma unroll
+                        for (int c = 0; c < kSlots; ++c) {
+                            const int stream = (u - c) & 3;
+                            const int at = stream * pr.refN4 - ((c > u) ? 1 : 0);
+                            const float4 x = __ldg(pX + at);
+                            const float4 y = __ldg(pX + at + yOff);
+                            r[c][0] = x.x; r[c][1] = x.y; r[c][2] = x.z; r[c][3] = x.w; r[c][4] = y.x; r[c][5] = y.y;
+                            gOpR[c] = y.z; gExR[c] = y.w;
+                            gapR = gapR || (y.y != 0.0f);
+                            gapQ = gapQ || (q[c][5] != 0.0f);
+                        }
+                    }
+                    numerators4<MC>(r, q, a, num);
+                    // gap-character terms (TALCO-XDrop.cpp:393-394): each loop adds exact zeros unless the query (resp.
+                    // reference) column holds gaps, so it is skipped when no lane of the warp needs it
+                    if (__any_sync(0xffffffffu, gapQ)) {
+#pragma unroll
+                        for (int c = 0; c < kSlots; ++c)
+#pragma unroll
+                            for (int l = 0; l < 5; ++l) num[c] = __fmaf_rn(__fmul_rn(r[c][l], q[c][5]), gapChar, num[c]);
+                    }
+                    if (__any_sync(0xffffffffu, gapR)) {
+#pragma unroll
+                        for (int c = 0; c < kSlots; ++c)
+#pragma unroll
+                            for (int m = 0; m < 5; ++m) num[c] = __fmaf_rn(__fmul_rn(r[c][5], q[c][m]), gapChar, num[c]);
+                    }
+                    if (divMode == 1) {
+                        // reciprocal-based exact division; numerators that are non-zero but tiny (|n| < 2^-60, where the
+                        // quotient or the FMA residual could leave the normal range) take the IEEE divide instead
+                        unsigned tiny = 0xffffffffu;
+#pragma unroll
+                        for (int c = 0; c < kSlots; ++c) tiny = min(tiny, (__float_as_uint(num[c]) & 0x7fffffffu) - 1u);
+                        if (tiny < 0x21800000u - 1u) {
+#pragma unroll
+                            for (int c = 0; c < kSlots; ++c) num[c] = __fdiv_rn(num[c], denom);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < kSlots; ++c) num[c] = exactDivNormal(num[c], denom, rcp);
+                        }
+                    } else if (divMode == 2) {
+#pragma unroll
+                        for (int c = 0; c < kSlots; ++c) num[c] = __fdiv_rn(num[c], denom);
+                    }
 
                     // match candidates: H[k-2][i-1] + sim when the diagonal neighbour is inside its band ...
                     float match[kSlots];
@@ -378,113 +321,93 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
                         tbWord |= (ptr | (insFromIns ? 4u : 0u) | (delFromDel ? 8u : 0u)) << (8 * c);
                     }
                     if (k <= marker && actBits) *reinterpret_cast<unsigned *>(tb + static_cast<size_t>(k) * W + rho0) = tbWord;
-
-                    if (k >= marker - 1) {                              // convergence pointers, reference indexing (:520-547)
-                        const int c0 = k % 3, c1 = (c0 + 2) % 3, c2 = (c0 + 1) % 3;
-                        if (k <= marker) {
-#pragma unroll
-                            for (int c = 0; c < kSlots; ++c) {
-                                if (actBits & (1u << c)) {
-                                    const int i = iBase + c, off = i - L0;
-                                    if (k == marker - 1) { cs[c] = (3 << 16) | (i & 0xFFFF); sCS[c0][off] = cs[c]; }
-                                    else {
-                                        cs[c] = (i & 0xFFFF); ci[c] = (1 << 16) | (i & 0xFFFF); cd[c] = (2 << 16) | (i & 0xFFFF);
-                                        sCS[c0][off] = cs[c]; sCI[g0][off] = ci[c]; sCD[g0][off] = cd[c];
-                                    }
-                                }
-                            }
-                        } else {
-                            // branch-free: every slot reads its five source slots at clamped offsets; only live cells store
-                            const int *pCIp = sCI[g1], *pCDp = sCD[g1], *pCS1 = sCS[c1], *pCS2 = sCS[c2];
-                            int *pCI = sCI[g0], *pCD = sCD[g0], *pCS = sCS[c0];
-#pragma unroll
-                            for (int c = 0; c < kSlots; ++c) {
-                                const int i = iBase + c;
-                                const int off = i - L0, offDiag = i - 1 - L2, offUp = i - L1, offLeft = offUp - 1;
-                                const int oL = min(max(offLeft, 0), CW - 1), oU = min(max(offUp, 0), CW - 1), oD = min(max(offDiag, 0), CW - 1);
-                                const unsigned nib = (tbWord >> (8 * c)) & 15u;
-                                const int aI = pCIp[oL], bI = pCS1[oL], aD = pCDp[oU], bD = pCS1[oU], dS = pCS2[oD];
-                                int vi = (nib & 4u) ? aI : ((bI != -1) ? bI : kInsBoundary);
-                                vi = (offLeft >= 0) ? vi : kInsBoundary;
-                                int vd = (nib & 8u) ? aD : ((bD != -1) ? bD : kDelBoundary);
-                                vd = (offUp >= 0) ? vd : kDelBoundary;
-                                const unsigned ptr = nib & 3u;
-                                const int vs = (ptr == 0u) ? ((offDiag >= 0) ? dS : -1) : ((ptr == 1u) ? vi : vd);
-                                ci[c] = vi; cd[c] = vd; cs[c] = vs;
-                                if (actBits & (1u << c)) { pCI[off] = vi; pCD[off] = vd; pCS[off] = vs; }
-                            }
-                        }
-                    }
                 } else {
 #pragma unroll
                     for (int c = 0; c < kSlots; ++c) h2[c] = h1[c];
                 }
                 leftHPrev = nbH;
 
-                // publish the warp's edge values and its reduction, then ARRIVE without waiting
+                int cs[kSlots], ci[kSlots], cd[kSlots];
+#pragma unroll
+                for (int c = 0; c < kSlots; ++c) cs[c] = ci[c] = cd[c] = 0;
+                const int c0 = k % 3;
+                if (k >= marker - 1 && __any_sync(0xffffffffu, actBits != 0)) {   // convergence pointers, reference indexing (:520-547)
+                    const int c1 = (c0 + 2) % 3, c2 = (c0 + 1) % 3;
+                    if (k <= marker) {
+#pragma unroll
+                        for (int c = 0; c < kSlots; ++c) {
+                            if (actBits & (1u << c)) {
+                                const int i = iBase + c, off = i - L0;
+                                if (k == marker - 1) { cs[c] = (3 << 16) | (i & 0xFFFF); sCS[c0][off] = cs[c]; }
+                                else {
+                                    cs[c] = (i & 0xFFFF); ci[c] = (1 << 16) | (i & 0xFFFF); cd[c] = (2 << 16) | (i & 0xFFFF);
+                                    sCS[c0][off] = cs[c]; sCI[g0][off] = ci[c]; sCD[g0][off] = cd[c];
+                                }
+                            }
+                        }
+                    } else {
+                        // branch-free: every slot reads its five source slots at clamped offsets; only live cells store
+                        const int *pCIp = sCI[g1], *pCDp = sCD[g1], *pCS1 = sCS[c1], *pCS2 = sCS[c2];
+                        int *pCI = sCI[g0], *pCD = sCD[g0], *pCS = sCS[c0];
+#pragma unroll
+                        for (int c = 0; c < kSlots; ++c) {
+                            const int i = iBase + c;
+                            const int off = i - L0, offDiag = i - 1 - L2, offUp = i - L1, offLeft = offUp - 1;
+                            const int oL = min(max(offLeft, 0), CW - 1), oU = min(max(offUp, 0), CW - 1), oD = min(max(offDiag, 0), CW - 1);
+                            const unsigned nib = (tbWord >> (8 * c)) & 15u;
+                            const int aI = pCIp[oL], bI = pCS1[oL], aD = pCDp[oU], bD = pCS1[oU], dS = pCS2[oD];
+                            int vi = (nib & 4u) ? aI : ((bI != -1) ? bI : kInsBoundary);
+                            vi = (offLeft >= 0) ? vi : kInsBoundary;
+                            int vd = (nib & 8u) ? aD : ((bD != -1) ? bD : kDelBoundary);
+                            vd = (offUp >= 0) ? vd : kDelBoundary;
+                            const unsigned ptr = nib & 3u;
+                            const int vs = (ptr == 0u) ? ((offDiag >= 0) ? dS : -1) : ((ptr == 1u) ? vi : vd);
+                            ci[c] = vi; cd[c] = vd; cs[c] = vs;
+                            if (actBits & (1u << c)) { pCI[off] = vi; pCD[off] = vd; pCS[off] = vs; }
+                        }
+                    }
+                }
+
+                // one barrier per diagonal: publish the warp's edge values and its reduction
                 const int wMax = __reduce_max_sync(0xffffffffu, orderedInt(myMax));
                 const int wLo = __reduce_min_sync(0xffffffffu, myLo);
                 const int wHi = __reduce_max_sync(0xffffffffu, myHi);
-                const unsigned wBad = __reduce_or_sync(0xffffffffu, pendBad);
                 if (lane == 31) edgeOut[g0 * 8] = make_float2(h1[kSlots - 1], i1[kSlots - 1]);
-                if (lane == 0) redOut[g0 * 8] = make_int4(wMax, wLo, wHi, static_cast<int>(wBad));
-                __syncwarp();                                           // the warp's shared-memory writes happen-before lane 0's release
-                if (lane == 0) mbarArrive(mbarAddr);
-
-                // while the other warps catch up: scores of diagonal k+1 for the rows this thread holds now (the band of
-                // k+1 lies inside [L0, U0+1]; if the thread is re-assigned meanwhile the scores are recomputed)
-                if (a.overlap && k + 1 < nDiag && __any_sync(0xffffffffu, (iBase <= U0 + 1) && (iBase + kSlots - 1 >= L0))) {
-                    scorePhase(k + 1, iBase);
-                    specBase = iBase;
-                }
-
-                mbarWait(mbarAddr, mbarPhase);
-                mbarPhase ^= 1u;
+                if (lane == 0) redOut[g0 * 8] = make_int4(wMax, wLo, wHi, 0);
+                __syncthreads();
                 int oMax = sh.red[g0][0].x, newL = sh.red[g0][0].y, newU = sh.red[g0][0].z;
-                unsigned badAll = static_cast<unsigned>(sh.red[g0][0].w);
 #pragma unroll
                 for (int w = 1; w < NW; ++w) {
                     const int4 t = sh.red[g0][w];
-                    oMax = max(oMax, t.x); newL = min(newL, t.y); newU = max(newU, t.z); badAll |= static_cast<unsigned>(t.w);
+                    oMax = max(oMax, t.x); newL = min(newL, t.y); newU = max(newU, t.z);
                 }
                 if (newL == 0x7fffffff) { newL = U0 + 1; newU = L0 - 1; }
-                const float maxPrimeBefore = maxScorePrime;
                 maxScorePrime = fmaxf(maxScorePrime, orderedFloat(oMax));
 
-                // late resolution of diagonal k-1's convergence test (:585-595, :609)
-                if (pend) {
-                    pend = false;
-                    const int cS = (badAll & 2u) ? -1 : pendS;
-                    if (!(badAll & 1u) && pendI == pendD && pendI == cS && prevConvS == cS && pendI != -1) {
-                        converged = true;
-                        convValue = prevConvS;
-                        convScore = pendMaxPrime;
-                        const float ms = (pendMaxPrime < 0.0f) ? 0.0f : pendMaxPrime;
-                        if (ms > convScore) {   // the reference would have stopped right there, on diagonal k-1: drop diagonal k
-                            stopped = true;
-                            tileCells -= lastWidth;
-                            lastK = k - 1;
-                            maxScorePrime = maxPrimeBefore;
-                            break;
-                        }
-                    }
-                    prevConvS = cS;
-                }
-                pendBad = 0;
-                if (!converged && k >= marker && k < nDiag - 1) {       // set up the test of this diagonal
-                    const int c0 = k % 3;
+                if (!converged && k >= marker && k < nDiag - 1) {       // :585-595
+                    const int c2 = (c0 + 1) % 3;
                     const int start = newL - L0;
-                    pendI = sCI[g0][start]; pendD = sCD[g0][start]; pendS = sCS[c0][start];
+                    const int vI = sCI[g0][start], vD = sCD[g0][start], vS = sCS[c0][start];
+                    unsigned bad = 0;
 #pragma unroll
                     for (int c = 0; c < kSlots; ++c) {
                         const int i = iBase + c;
                         if ((actBits & (1u << c)) && i > newL && i <= newU) {
-                            if (ci[c] != pendI || cd[c] != pendD) pendBad |= 1u;
-                            if (cs[c] != pendS) pendBad |= 2u;
+                            if (ci[c] != vI || cd[c] != vD) bad |= 1u;
+                            if (cs[c] != vS) bad |= 2u;
                         }
                     }
-                    pend = true;
-                    pendMaxPrime = maxScorePrime;
+                    if (bad) atomicAnd(&sh.convMask[c0], ~bad);
+                    if (tid == 0) sh.convMask[c2] = 3u;
+                    __syncthreads();
+                    const unsigned ok = sh.convMask[c0];
+                    const int cS = (ok & 2u) ? vS : -1;
+                    if ((ok & 1u) && vI == vD && vI == cS && prevConvS == cS && vI != -1) {
+                        converged = true;
+                        convValue = prevConvS;
+                        convScore = maxScorePrime;
+                    }
+                    prevConvS = cS;
                 }
 
                 L2 = L1; U2 = U1; L1 = L0; U1 = U0;

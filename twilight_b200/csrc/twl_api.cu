@@ -292,9 +292,6 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
         a.overflowCount = hasNext ? ctx->dCounters.ptr + 2 * (s + 1) + 1 : nullptr;
         a.tbStride = st.tbStride;
         a.stateCap = st.cap;
-        // few pairs (a partial wave of CTAs): the kernel is latency bound, overlap score computation with the barrier;
-        // many pairs: other CTAs already fill the wait, and the speculative scores would only add instructions
-        a.overlap = (ctx->overlapMode >= 0) ? ctx->overlapMode : ((n <= st.grid) ? 1 : 0);
         a.stateScratch = (st.kind == 2) ? ctx->dState.ptr : nullptr;
         a.stateStride = (st.kind == 2) ? twl::genericStateWords(st.cap) : 0;
         if (st.kind == 0) TWL_CUDA(ctx, twl::launchTalcoWavefront(st.threads, matClass, a, st.grid, ctx->stream));
@@ -363,7 +360,6 @@ int twl_align_profiles(twl_ctx *ctx, const twl_profile_pair *pairs, int n_pairs,
 int twl_set_option(twl_ctx *ctx, const char *name, int value) {
     if (!ctx || !name) return TWL_E_ARG;
     if (std::strcmp(name, "force_generic") == 0) { ctx->forceGeneric = value != 0; return TWL_OK; }
-    if (std::strcmp(name, "overlap") == 0) { ctx->overlapMode = value; return TWL_OK; }   // -1 auto, 0 off, 1 on
     return fail(ctx, TWL_E_ARG, std::string("twl_set_option: unknown option ") + name);
 }
 

@@ -78,7 +78,6 @@ struct twl_ctx {
     DevBuf<uint8_t> dTb;
     DevBuf<float> dState;
 
-    int overlapMode = -1;        // wavefront kernel score/barrier overlap: -1 auto, 0 off, 1 on
     bool forceGeneric = false;   // route nucleotide batches through the generic kernel (A/B parity + benchmarking)
     float lastMs = -1.0f;
     int lastLaunches = 0;

@@ -70,7 +70,6 @@ struct TalcoArgs {
     float *stateScratch;     // per-CTA wavefront state when it does not fit in shared memory
     size_t stateStride;      // in 4-byte words
     int stateCap;            // cells per wavefront array (excluding padding)
-    int overlap;             // wavefront kernel: compute the next diagonal's scores while the barrier of this one completes
 };
 
 } // namespace twl
