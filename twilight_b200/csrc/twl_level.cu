@@ -5,6 +5,9 @@
 
 #include <algorithm>
 #include <cstring>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <numeric>
 #include <thread>
 
@@ -72,6 +75,18 @@ TwlLevelState *levelOf(twl_ctx *ctx) {
         for (auto &e : ctx->level->ev) cudaEventCreate(&e);
     }
     return ctx->level;
+}
+
+// splits [0, n) over a few host threads (staging copies of many small rows are memory-latency bound on one core)
+template <typename F>
+void parallelRows(int n, size_t bytes, const F &body) {
+    const int nThreads = (bytes > (static_cast<size_t>(4) << 20)) ? static_cast<int>(std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()))) : 1;
+    if (nThreads == 1) { body(0, n); return; }
+    std::vector<std::thread> pool;
+    const int per = (n + nThreads - 1) / nThreads;
+    for (int t = 1; t < nThreads; ++t) pool.emplace_back([&, t] { body(std::min(n, t * per), std::min(n, (t + 1) * per)); });
+    body(0, std::min(n, per));
+    for (auto &th : pool) th.join();
 }
 
 cudaError_t poolAlloc(TwlLevelState *L, size_t bytes, char **out) {
@@ -220,7 +235,7 @@ int twl_rows_upload(twl_ctx *ctx, int n, const int32_t *ids, const char *const *
     TWL_CUDA(ctx, L->hStage.reserve(std::max<size_t>(total, 16)));
     TWL_CUDA(ctx, L->dStage.reserve(std::max<size_t>(total, 16)));
     TWL_CUDA(ctx, L->dCopies.reserve(n));
-    for (int i = 0; i < n; ++i) std::memcpy(L->hStage.ptr + list[i].stageOff, rows[i], lens[i]);
+    parallelRows(n, total, [&](int b, int e) { for (int i = b; i < e; ++i) std::memcpy(L->hStage.ptr + list[i].stageOff, rows[i], lens[i]); });
     TWL_CUDA(ctx, cudaMemcpyAsync(L->dStage.ptr, L->hStage.ptr, total, cudaMemcpyHostToDevice, ctx->stream));
     TWL_CUDA(ctx, cudaMemcpyAsync(L->dCopies.ptr, list.data(), sizeof(twl::RowCopy) * n, cudaMemcpyHostToDevice, ctx->stream));
     twl::rowTransferKernel<<<(n * 32 + 255) / 256, 256, 0, ctx->stream>>>(L->dCopies.ptr, n, L->dStage.ptr, 1);
@@ -257,10 +272,12 @@ int twl_rows_download(twl_ctx *ctx, int n, const int32_t *ids, char *const *dst,
     TWL_CUDA(ctx, cudaGetLastError());
     TWL_CUDA(ctx, cudaMemcpyAsync(L->hStage.ptr, L->dStage.ptr, total, cudaMemcpyDeviceToHost, ctx->stream));
     TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    for (int i = 0; i < n; ++i) {
-        std::memcpy(dst[i], L->hStage.ptr + list[i].stageOff, list[i].len);
-        if (lens) lens[i] = list[i].len;
-    }
+    parallelRows(n, total, [&](int b, int e) {
+        for (int i = b; i < e; ++i) {
+            std::memcpy(dst[i], L->hStage.ptr + list[i].stageOff, list[i].len);
+            if (lens) lens[i] = list[i].len;
+        }
+    });
     return TWL_OK;
 }
 
@@ -279,10 +296,24 @@ namespace {
 
 struct ChunkPlan { int begin, end; };
 
+// TWL_TRACE=1: wall-clock of the host-side steps of a level chunk on stderr
+struct Trace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    Trace() : on(std::getenv("TWL_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *what) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[twl] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 template <int P>
 int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, int begin, int end, int task, float threshold,
                   int cacheTh, int8_t *const *paths, twl_level_result *results, int chunkNo) {
     using namespace twl;
+    Trace tr;
     const int n = end - begin;
     const int nSides = 2 * n;
     const char type = (P == 6) ? 'n' : 'p';
@@ -350,6 +381,7 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
         maxF = std::max(maxF, std::min(q.fLen, std::min(in.ref.aln_len, in.qry.aln_len)));
     }
 
+    tr.mark("describe level (host)");
     // ---- upload the level description
     TWL_CUDA(ctx, L->dSides.reserve(nSides));
     TWL_CUDA(ctx, L->dRowIn.reserve(std::max<size_t>(rowIn.size(), 1)));
@@ -403,6 +435,7 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
     char *hCons = L->hConsPin.ptr;
     std::vector<std::vector<int8_t>> finalPath(n);
 
+    tr.mark("reserve + H2D description");
     // ---- phase 1: profiles + consensus (+ msaFreq cache); phase 2: gappy-column compaction + PSGP + DP packing
     TWL_CUDA(ctx, cudaEventRecord(L->ev[0], ctx->stream));
     {
@@ -470,6 +503,7 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
     }
 
     // ---- host: gappy columns back (helper.cpp:324-375), build the update list
+    tr.mark("kernels + D2H results");
     // (a) per pair, independent: restore the removed column runs -> final path (host threads)
     std::vector<char> aligned(n, 0);
     {
@@ -510,6 +544,7 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
             for (auto &th : pool) th.join();
         }
     }
+    tr.mark("gappy restore (host threads)");
     // (b) serial: the update list
     std::vector<DevUpdate> ups;
     std::vector<const char *> updIn;
@@ -572,6 +607,7 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
         updPair.push_back(p);
     }
 
+    tr.mark("build update list (host)");
     // ---- phase 4: row update + frequency merge
     bool updateTimed = false;
     if (!ups.empty()) {
@@ -621,6 +657,7 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
     for (size_t k = 0; k < ups.size(); ++k)
         if (ups[k].mergedOff >= 0)
             L->keep[begin + updPair[k]].merged.assign(hMerged.begin() + ups[k].mergedOff, hMerged.begin() + ups[k].mergedOff + static_cast<size_t>(ups[k].pathLen) * P);
+    tr.mark("update kernels + D2H freq");
     for (int i = 0; i < 3; ++i) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, L->ev[i], L->ev[i + 1]);
