@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(kLvlThreads) gappyCompactKernel(DevSide *sides
     const float openScaled = __fmul_rn(gapOpen, scale);
 
     int keptBase = 0, runBase = 0;
+    bool oneHot = true;   // every kept column of this thread is one-hot (count 1.0 on one of the first P-1... letters, no gap)
     for (int c0 = 0; c0 < sd.alnLen; c0 += kLvlThreads) {
         const int t = c0 + threadIdx.x;
         const bool live = t < sd.alnLen;
@@ -212,6 +213,12 @@ __global__ void __launch_bounds__(kLvlThreads) gappyCompactKernel(DevSide *sides
         const int idx = keptBase + blockExclusiveScan(isKept, warpSums, &chunkKept);
         const int runIdxIncl = runBase + blockExclusiveScan(isStart, warpSums, &chunkStarts) + isStart;
         if (isKept) {
+            if (P == 6) {
+                int ones = 0, zeros = 0;
+#pragma unroll
+                for (int x = 0; x < 5; ++x) { ones += (v[x] == 1.0f); zeros += (v[x] == 0.0f); }
+                oneHot = oneHot && (ones == 1) && (zeros == 4) && (v[5] == 0.0f);
+            }
             // calculatePSGP, helper.cpp:185-196 (the ratio is evaluated in double, as upstream)
             const float g = v[P - 1];
             float gOp = gapOpen, gEx = gapExtend;
@@ -240,7 +247,7 @@ __global__ void __launch_bounds__(kLvlThreads) gappyCompactKernel(DevSide *sides
         keptBase += chunkKept;
         runBase += chunkStarts;
     }
-    __syncthreads();
+    const int allOneHot = __syncthreads_and(oneHot ? 1 : 0);
     for (int g = threadIdx.x; g < runBase; g += kLvlThreads) {
         int *r = runs + sd.runsOff + 2 * g;
         r[1] = r[1] - r[0] + 1;
@@ -251,6 +258,7 @@ __global__ void __launch_bounds__(kLvlThreads) gappyCompactKernel(DevSide *sides
         DevPair &pr = pairs[sd.pairIdx];
         if (sd.isQry) { pr.qryLen = newLen; pr.qryN4 = n4; }
         else { pr.refLen = newLen; pr.refN4 = n4; }
+        if (P == 6 && allOneHot && newLen > 0) atomicOr(&pr.pad, sd.isQry ? kQryOneHot : kRefOneHot);   // DP fast path, talco_wavefront.cu
     }
     (void)sTotal;
 }

@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
         // 0: denominator is 1 (no division), 1: reciprocal-based exact division, 2: IEEE divide (mantissa of all ones)
         const int divMode = (denom == 1.0f) ? 0 : (((__float_as_int(denom) & 0x7fffff) == 0x7fffff) ? 2 : 1);
         const float gapChar = pr.gapChar;
+        const int kind = pr.pad;   // kRefOneHot | kQryOneHot
         int refOff = 0, qryOff = 0, tile = 0, outPos = 0, status = 0;
         unsigned long long cells = 0, diagonals = 0;
         bool lastTile = false;
@@ -205,6 +206,27 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
                         const float4 y = __ldg(qryY + at);
                         q[c][0] = x.x; q[c][1] = x.y; q[c][2] = x.z; q[c][3] = x.w; q[c][4] = y.x; q[c][5] = y.y;
                         gOpQ[c] = y.z; gExQ[c] = y.w;
+                        if (kind) {
+                            // w[a] = sum over m of q[m]*S[a][m] in the reference's order: the whole contraction of this row
+                            // against a one-hot reference column of letter a (kRefOneHot), or simply S[a][b] when the row
+                            // itself is one-hot at b (kQryOneHot).
+                            float w[5];
+#pragma unroll
+                            for (int l = 0; l < 5; ++l)
+                                w[l] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(q[c][0], a.scoreNt[l * 5 + 0]), __fmul_rn(q[c][1], a.scoreNt[l * 5 + 1])),
+                                                 __fmul_rn(q[c][2], a.scoreNt[l * 5 + 2])), __fmul_rn(q[c][3], a.scoreNt[l * 5 + 3])), __fmul_rn(q[c][4], a.scoreNt[l * 5 + 4]));
+                            if (kind & kRefOneHot) {
+                                // + the one surviving gap-character term (TALCO-XDrop.cpp:393 with r[a] = 1), then the division
+#pragma unroll
+                                for (int l = 0; l < 5; ++l) {
+                                    const float n = __fmaf_rn(q[c][5], gapChar, w[l]);
+                                    w[l] = (divMode == 0) ? n : __fdiv_rn(n, denom);
+                                }
+                            }
+#pragma unroll
+                            for (int l = 0; l < 5; ++l) q[c][l] = w[l];
+                            q[c][5] = 0.0f;
+                        }
                     }
                 }
 
@@ -238,22 +260,47 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
                             gapQ = gapQ || (q[c][5] != 0.0f);
                         }
                     }
-                    numerators4<MC>(r, q, a, num);
-                    // gap-character terms (TALCO-XDrop.cpp:393-394): each loop adds exact zeros unless the query (resp.
-                    // reference) column holds gaps, so it is skipped when no lane of the warp needs it
-                    if (__any_sync(0xffffffffu, gapQ)) {
+                    if (kind & kRefOneHot) {
+                        // The reference side is a single gap-free sequence: its columns are exactly one-hot (count 1.0), so
+                        // every term of the reference's sum except those of the one present letter is an exact zero, and
+                        // the similarity depends only on (query row, reference letter). q[c][a] holds that value for
+                        // letter a (computed when the row was fetched, see below); the FMA chain just picks it.
 #pragma unroll
                         for (int c = 0; c < kSlots; ++c)
+                            num[c] = __fmaf_rn(r[c][4], q[c][4], __fmaf_rn(r[c][3], q[c][3], __fmaf_rn(r[c][2], q[c][2],
+                                     __fmaf_rn(r[c][1], q[c][1], __fmul_rn(r[c][0], q[c][0])))));
+                    } else if (kind & kQryOneHot) {
+                        // The query side is one-hot: q[c][l] holds S[l][b] for the row's letter b; the surviving terms are
+                        // S[l][b]*r[l], summed in the reference's order, then the one non-zero gap term and the division.
 #pragma unroll
-                            for (int l = 0; l < 5; ++l) num[c] = __fmaf_rn(__fmul_rn(r[c][l], q[c][5]), gapChar, num[c]);
+                        for (int c = 0; c < kSlots; ++c) {
+                            float n = __fmul_rn(q[c][0], r[c][0]);
+                            n = __fadd_rn(n, __fmul_rn(q[c][1], r[c][1]));
+                            n = __fadd_rn(n, __fmul_rn(q[c][2], r[c][2]));
+                            n = __fadd_rn(n, __fmul_rn(q[c][3], r[c][3]));
+                            n = __fadd_rn(n, __fmul_rn(q[c][4], r[c][4]));
+                            num[c] = __fmaf_rn(r[c][5], gapChar, n);
+                        }
+                    } else {
+                        numerators4<MC>(r, q, a, num);
+                        // gap-character terms (TALCO-XDrop.cpp:393-394): each loop adds exact zeros unless the query (resp.
+                        // reference) column holds gaps, so it is skipped when no lane of the warp needs it
+                        if (__any_sync(0xffffffffu, gapQ)) {
+#pragma unroll
+                            for (int c = 0; c < kSlots; ++c)
+#pragma unroll
+                                for (int l = 0; l < 5; ++l) num[c] = __fmaf_rn(__fmul_rn(r[c][l], q[c][5]), gapChar, num[c]);
+                        }
+                        if (__any_sync(0xffffffffu, gapR)) {
+#pragma unroll
+                            for (int c = 0; c < kSlots; ++c)
+#pragma unroll
+                                for (int m = 0; m < 5; ++m) num[c] = __fmaf_rn(__fmul_rn(r[c][5], q[c][m]), gapChar, num[c]);
+                        }
                     }
-                    if (__any_sync(0xffffffffu, gapR)) {
-#pragma unroll
-                        for (int c = 0; c < kSlots; ++c)
-#pragma unroll
-                            for (int m = 0; m < 5; ++m) num[c] = __fmaf_rn(__fmul_rn(r[c][5], q[c][m]), gapChar, num[c]);
-                    }
-                    if (divMode == 1) {
+                    if (kind & kRefOneHot) {
+                        // already divided when the row was fetched
+                    } else if (divMode == 1) {
                         // reciprocal-based exact division; numerators that are non-zero but tiny (|n| < 2^-60, where the
                         // quotient or the FMA residual could leave the normal range) take the IEEE divide instead
                         unsigned tiny = 0xffffffffu;

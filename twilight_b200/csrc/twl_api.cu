@@ -44,19 +44,24 @@ size_t sideWords(int len, int P) {
     return static_cast<size_t>(len) * (P + 2);
 }
 
-void packColumns(float *dst, const float *freq, const float *gapOp, const float *gapEx, int len, int P) {
+// returns true when every column of a nucleotide side is exactly one-hot (one of A,C,G,T,N = 1.0, everything else 0)
+bool packColumns(float *dst, const float *freq, const float *gapOp, const float *gapEx, int len, int P) {
     const int PW = P + 2;
     if (P == 6) {   // de-interleaved nucleotide layout, see twl_device.cuh
         const int n4 = (len + 3) / 4;
         std::memset(dst, 0, sideWords(len, P) * sizeof(float));
+        bool oneHot = true;
         for (int c = 0; c < len; ++c) {
             float *x = dst + twl::ntColIndex(c, n4) * 4;
             float *y = x + static_cast<size_t>(16) * n4;
             const float *f = freq + static_cast<size_t>(c) * 6;
             x[0] = f[0]; x[1] = f[1]; x[2] = f[2]; x[3] = f[3];
             y[0] = f[4]; y[1] = f[5]; y[2] = gapOp[c]; y[3] = gapEx[c];
+            int ones = 0, zeros = 0;
+            for (int v = 0; v < 5; ++v) { ones += (f[v] == 1.0f); zeros += (f[v] == 0.0f); }
+            oneHot = oneHot && ones == 1 && zeros == 4 && f[5] == 0.0f;
         }
-        return;
+        return oneHot;
     }
     for (int c = 0; c < len; ++c) {
         float *d = dst + static_cast<size_t>(c) * PW;
@@ -64,6 +69,7 @@ void packColumns(float *dst, const float *freq, const float *gapOp, const float 
         d[P] = gapOp[c];
         d[P + 1] = gapEx[c];
     }
+    return false;
 }
 
 } // namespace
@@ -190,8 +196,9 @@ int twl_batch_stage(twl_ctx *ctx, const twl_profile_pair *pairs, int n_pairs) {
         auto work = [&](int t) {
             for (int p = t; p < n_pairs; p += nThreads) {
                 const twl_profile_pair &in = pairs[p];
-                packColumns(ctx->hProf.ptr + ctx->hPairs[p].refOff, in.freq_ref, in.gap_open_ref, in.gap_ext_ref, in.ref_len, P);
-                packColumns(ctx->hProf.ptr + ctx->hPairs[p].qryOff, in.freq_qry, in.gap_open_qry, in.gap_ext_qry, in.qry_len, P);
+                const bool r1 = packColumns(ctx->hProf.ptr + ctx->hPairs[p].refOff, in.freq_ref, in.gap_open_ref, in.gap_ext_ref, in.ref_len, P);
+                const bool q1 = packColumns(ctx->hProf.ptr + ctx->hPairs[p].qryOff, in.freq_qry, in.gap_open_qry, in.gap_ext_qry, in.qry_len, P);
+                ctx->hPairs[p].pad = (r1 ? twl::kRefOneHot : 0) | (q1 ? twl::kQryOneHot : 0);
             }
         };
         if (nThreads == 1) work(0);

@@ -24,6 +24,8 @@ namespace twl {
 constexpr int kMaxMarker = 1024;          // Talco_xdrop::Params::marker, TALCO-XDrop.cpp:51
 constexpr int kInsBoundary = -2;          // I_BOUNDARY, TALCO-XDrop.cpp:33
 constexpr int kDelBoundary = -3;          // D_BOUNDARY, TALCO-XDrop.cpp:34
+constexpr int kRefOneHot = 1;             // every ref column is exactly one-hot: one of A,C,G,T,N has count 1.0, all else 0
+constexpr int kQryOneHot = 2;
 constexpr int kStatusEmptySide = 200;     // internal: one side has no columns
 constexpr int kStatusRetryWide = 100;     // internal: band exceeded this kernel's state capacity, rerun on the wide variant
 
@@ -35,7 +37,7 @@ struct DevPair {
     float refNum, qryNum;
     float gapChar;
     int xdrop, fLen;
-    int pad;
+    int pad;            // nucleotide fast-path flags: kRefOneHot / kQryOneHot (set by the packers when a side is a single gap-free sequence)
     int refN4, qryN4;   // nucleotide layout: stream length ceil(len/4) of each side
 };
 
