@@ -293,6 +293,10 @@ def main():
         dp_gcups_gpu = cells * args.steps / (phases[2] * 1e-3) / 1e9            # dominant kernel, this rank
         achieved_tflops = dp_gcups_gpu * 1e9 * FLOP_PER_CELL_NT / 1e12
         n_seqs = len(ids) * world
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath):   # DRAM bytes per cell of the dominant kernel from the committed ncu --set full capture
+            traffic = json.load(open(tpath))["dram_bytes_per_cell"] * cells
         line = {"metric": "dp_gcups", "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
@@ -308,7 +312,7 @@ def main():
                 "phase_ms_per_step": {"profile_build": phases[0] / args.steps, "gappy_psgp_pack": phases[1] / args.steps,
                                       "dp_chain": phases[2] / args.steps, "row_update_freq_merge": phases[3] / args.steps},
                 "roofline": {"bound": "fp32-pipe", "achieved": achieved_tflops, "peak": pk["fp32_tflops"], "unit": "TFLOP/s",
-                             "frac": achieved_tflops / pk["fp32_tflops"], "traffic": None, "kernel": "talcoWavefrontKernel<128,1>",
+                             "frac": achieved_tflops / pk["fp32_tflops"], "traffic": traffic, "kernel": "talcoWavefrontKernel<128,1>",
                              "note": f"dominant kernel (DP) is CUDA-core bound (SURVEY.md §8d): 117 FP32 op per cell x {dp_gcups_gpu:.1f} GCUPS "
                                      f"in the DP phase; peak = 148 SM x 128 lanes x 2 x {pk['sm_mhz']:.0f} MHz ({pk['source']} sm_max_mhz); per GPU"},
                 "seqs_per_s": n_seqs * args.steps / (dev_all * 1e-3),
