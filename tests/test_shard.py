@@ -73,3 +73,43 @@ def test_two_rank_gloo_level_shard(tmp_path):
     want = sum(ol.port_talco(cfg, p["freq_ref"], p["freq_qry"], p["gap_open_ref"], p["gap_ext_ref"], p["gap_open_qry"], p["gap_ext_qry"],
                              p["ref_num"], p["qry_num"])[2] for p in raw)
     assert n == 10 and slowest == 5 and cells == want
+
+
+def _msa_worker(rank, world, port, out_path):
+    import pickle
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from tests.fake_ctx import FakeContext
+    from twilight_b200 import msa, synth
+    tree = synth.random_tree(24, seed=9, mean_blen=0.05)
+    seqs = synth.evolve(tree, 200, seed=9)
+    w = np.random.default_rng(2).uniform(0.5, 1.5, 24).astype(np.float32)
+    rows, st, root_owner = msa.progressive_align_sharded(FakeContext(), tree, seqs, w, dist)
+    if rank == root_owner:
+        pickle.dump((rows, st.aln_len), open(out_path, "wb"))
+    counts = [None] * world
+    dist.all_gather_object(counts, st.pairs)
+    assert sum(counts) == 23 and min(counts) > 0          # every rank aligned something, nothing was aligned twice
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_msa_equals_single_process(tmp_path):
+    """Subtree sharding + node migration over gloo (world_size 2) gives the same MSA as one process."""
+    import pickle
+    import torch.multiprocessing as mp
+    from tests.fake_ctx import FakeContext
+    from twilight_b200 import msa, synth
+    out = str(tmp_path / "rows.pkl")
+    port = 29500 + ((os.getpid() + 7) % 2000)
+    mp.spawn(_msa_worker, args=(2, port, out), nprocs=2, join=True)
+    rows2, aln_len2 = pickle.load(open(out, "rb"))
+    tree = synth.random_tree(24, seed=9, mean_blen=0.05)
+    seqs = synth.evolve(tree, 200, seed=9)
+    w = np.random.default_rng(2).uniform(0.5, 1.5, 24).astype(np.float32)
+    rows1, st1 = msa.progressive_align(FakeContext(), tree, seqs, w)
+    assert aln_len2 == st1.aln_len
+    assert rows2 == rows1
