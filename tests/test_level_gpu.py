@@ -110,3 +110,20 @@ def test_progressive_driver_end_to_end():
     assert [r.replace(b"-", b"") for r in rows] == list(seqs)
     # same rows as the oracle (the oracle lists ref members first at every merge; compare as a multiset keyed by content)
     assert sorted(rows) == sorted(root.rows)
+
+
+def test_level_is_chunked_transparently(monkeypatch):
+    """A level larger than the scratch budget is processed in several chunks; results and rows must not depend on it."""
+    import twilight_b200
+    from twilight_b200 import msa
+    n, L = 64, 400
+    tree = synth.random_tree(n, seed=21, mean_blen=0.05, shape="balanced")
+    seqs = synth.evolve(tree, L, seed=21)
+    w = np.ones(n, np.float32)
+    ctx = twilight_b200.Context()
+    rows_a, st_a = msa.progressive_align(ctx, tree, seqs, w)
+    monkeypatch.setenv("TWL_LEVEL_BUDGET_MB", "1")      # ~6 pairs per chunk at the first level
+    rows_b, st_b = msa.progressive_align(ctx, tree, seqs, w)
+    ctx.close()
+    assert rows_a == rows_b and st_a.cells == st_b.cells and st_a.aln_len == st_b.aln_len
+    assert st_b.launches > st_a.launches

@@ -690,7 +690,8 @@ int twl_align_level(twl_ctx *ctx, const twl_level_pair *pairs, int n_pairs, int 
     for (float &m : L->phaseMs) m = 0.f;
     if (cache_threshold <= 0) cache_threshold = 1000;
     // chunk the level so that the scratch (raw profiles dominate: 4*P bytes per column and side) stays bounded
-    const size_t budget = static_cast<size_t>(12) << 30;
+    size_t budget = static_cast<size_t>(12) << 30;
+    if (const char *e = std::getenv("TWL_LEVEL_BUDGET_MB")) budget = static_cast<size_t>(std::max(1, std::atoi(e))) << 20;   // tests force small chunks
     int begin = 0, chunkNo = 0;
     while (begin < n_pairs) {
         int end = begin;
