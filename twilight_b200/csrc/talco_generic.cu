@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kGenThreads) talcoGenericKernel(const TalcoArg
         if (pr.refLen < 1 || pr.qryLen < 1) {   // an empty side (after gappy-column removal): nothing to align, the host emits the trivial path
             if (tid == 0) {
                 DevResult res;
-                res.status = kStatusEmptySide; res.pathLen = 0; res.tiles = 0; res.pad = 0; res.cells = 0; res.diagonals = 0;
+                res.status = kStatusEmptySide; res.pathLen = 0; res.tiles = 0; res.pad = 0; res.cells = 0; res.diagonals = 0; res.resRefOff = 0; res.resQryOff = 0;
                 a.results[pairIdx] = res;
             }
             continue;
@@ -121,10 +121,19 @@ __global__ void __launch_bounds__(kGenThreads) talcoGenericKernel(const TalcoArg
         int refOff = 0, qryOff = 0, tile = 0, outPos = 0, status = 0;
         unsigned long long cells = 0, diagonals = 0;
         bool lastTile = false;
+        if (a.resume) {   // the previous kernel of the chain finished some tiles of this pair before its band capacity ran out
+            const DevResult prev = a.results[pairIdx];
+            if (prev.status == kStatusRetryWide) {
+                refOff = prev.resRefOff; qryOff = prev.resQryOff; tile = prev.tiles; outPos = prev.pathLen;
+                cells = prev.cells; diagonals = prev.diagonals;
+            }
+        }
+        __syncthreads();   // every thread has read the previous result before thread 0 overwrites it at the end
 
         while (!lastTile) {                                                // Align_freq, :77-106
             const int refLen = pr.refLen - refOff, qryLen = pr.qryLen - qryOff;
             const int cap = min(pr.fLen, min(refLen, qryLen));             // :258
+            const unsigned long long cellsAtTile = cells, diagAtTile = diagonals;
             // wavefront state init, :301-308
             for (int t = tid; t < capPad; t += kGenThreads) {
                 S[0][t] = S[1][t] = S[2][t] = -1.0f;
@@ -269,6 +278,7 @@ __global__ void __launch_bounds__(kGenThreads) talcoGenericKernel(const TalcoArg
             }
 
             if (error) {
+                if (error == kStatusRetryWide) { cells = cellsAtTile; diagonals = diagAtTile; }   // the wide variant redoes this tile
                 status = error;
                 break;
             }
@@ -372,6 +382,8 @@ __global__ void __launch_bounds__(kGenThreads) talcoGenericKernel(const TalcoArg
             res.pad = 0;
             res.cells = cells;
             res.diagonals = diagonals;
+            res.resRefOff = refOff; res.resQryOff = qryOff;
+            if (status == kStatusRetryWide) res.pathLen = outPos;
             a.results[pairIdx] = res;
         }
     }

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
         if (pr.refLen < 1 || pr.qryLen < 1) {   // an empty side (after gappy-column removal): nothing to align, the host emits the trivial path
             if (tid == 0) {
                 DevResult res;
-                res.status = kStatusEmptySide; res.pathLen = 0; res.tiles = 0; res.pad = 0; res.cells = 0; res.diagonals = 0;
+                res.status = kStatusEmptySide; res.pathLen = 0; res.tiles = 0; res.pad = 0; res.cells = 0; res.diagonals = 0; res.resRefOff = 0; res.resQryOff = 0;
                 a.results[pairIdx] = res;
             }
             continue;
@@ -129,6 +129,14 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
         int refOff = 0, qryOff = 0, tile = 0, outPos = 0, status = 0;
         unsigned long long cells = 0, diagonals = 0;
         bool lastTile = false;
+        if (a.resume) {   // the previous kernel of the chain finished some tiles of this pair before its band capacity ran out
+            const DevResult prev = a.results[pairIdx];
+            if (prev.status == kStatusRetryWide) {
+                refOff = prev.resRefOff; qryOff = prev.resQryOff; tile = prev.tiles; outPos = prev.pathLen;
+                cells = prev.cells; diagonals = prev.diagonals;
+            }
+        }
+        __syncthreads();   // every thread has read the previous result before thread 0 overwrites it at the end
 
         while (!lastTile) {
             const int refLen = pr.refLen - refOff, qryLen = pr.qryLen - qryOff;
@@ -464,8 +472,10 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
                 lastK = k;
                 if (converged && maxScore > convScore) { stopped = true; break; }
             }
-            cells += tileCells;
-            diagonals += static_cast<unsigned long long>(lastK + 1);
+            if (error != kStatusRetryWide) {   // a tile that has to be redone by a wider kernel is not counted here
+                cells += tileCells;
+                diagonals += static_cast<unsigned long long>(lastK + 1);
+            }
             const int nStored = min(lastK, marker) + 1;
 
             if (error) { status = error; break; }
@@ -550,6 +560,8 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 1)) talcoWavefront
             res.pad = 0;
             res.cells = cells;
             res.diagonals = diagonals;
+            res.resRefOff = refOff; res.resQryOff = qryOff;
+            if (status == kStatusRetryWide) { res.pathLen = outPos; }
             a.results[pairIdx] = res;
         }
     }

@@ -299,6 +299,7 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
         a.overflowCount = hasNext ? ctx->dCounters.ptr + 2 * (s + 1) + 1 : nullptr;
         a.tbStride = st.tbStride;
         a.stateCap = st.cap;
+        a.resume = (s > 0) ? 1 : 0;
         a.stateScratch = (st.kind == 2) ? ctx->dState.ptr : nullptr;
         a.stateStride = (st.kind == 2) ? twl::genericStateWords(st.cap) : 0;
         if (st.kind == 0) TWL_CUDA(ctx, twl::launchTalcoWavefront(st.threads, matClass, a, st.grid, ctx->stream));

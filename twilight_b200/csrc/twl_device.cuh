@@ -46,11 +46,12 @@ __host__ __device__ inline long long ntColIndex(int j, int n4) { return static_c
 
 struct DevResult {
     int status;
-    int pathLen;
-    int tiles;
+    int pathLen;        // with status kStatusRetryWide: ops already written for the completed tiles
+    int tiles;          //                               number of completed tiles
     int pad;
-    unsigned long long cells;
+    unsigned long long cells;       // completed tiles only
     unsigned long long diagonals;
+    int resRefOff, resQryOff;       // with status kStatusRetryWide: where the failing tile starts; the next kernel of the chain resumes there
 };
 
 struct TalcoArgs {
@@ -72,6 +73,7 @@ struct TalcoArgs {
     float *stateScratch;     // per-CTA wavefront state when it does not fit in shared memory
     size_t stateStride;      // in 4-byte words
     int stateCap;            // cells per wavefront array (excluding padding)
+    int resume;              // this stage works on an overflow list: pairs continue at the tile recorded in `results`
 };
 
 } // namespace twl
