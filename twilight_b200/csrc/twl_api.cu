@@ -20,6 +20,10 @@ int wavefrontWindow(int threads);
 int nucleotideMatrixClass(const float *score5x5);
 cudaError_t launchTalcoWavefront(int threads, int matClass, const TalcoArgs &args, int grid, cudaStream_t stream);
 int wavefrontMaxCtasPerSm(int threads, int matClass);
+int warpKernelBandCapacity();
+int warpKernelWindow();
+cudaError_t launchTalcoWarp(int matClass, const TalcoArgs &args, int grid, cudaStream_t stream);
+int warpKernelMaxCtasPerSm(int matClass);
 cudaError_t launchDivSelfTest(const float *num, const float *den, int n, int *mismatches, cudaStream_t stream);
 } // namespace twl
 
@@ -245,12 +249,19 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
     const int marker = ctx->marker;
     const int wideCap = std::max(wideCapIn, 8);                     // widest band any pair of the batch may legally reach
     const bool nucleotide = (ctx->P == 6) && !ctx->forceGeneric;
-    struct Stage { int kind; int threads; int cap; int grid; size_t tbStride; };   // kind 0 wavefront, 1 generic smem, 2 generic global
+    struct Stage { int kind; int threads; int cap; int grid; size_t tbStride; };   // kind 0 wavefront (CTA per pair), 1 generic smem, 2 generic global, 3 warp per pair
     const int matClass = nucleotide ? twl::nucleotideMatrixClass(ctx->hScore.data()) : 0;
     std::vector<Stage> stages;
     auto tbRows = [&](int w) { return (static_cast<size_t>(marker + 1) * w + 255) & ~static_cast<size_t>(255); };
+    // many pairs: throughput kernel (one pair per warp) first; few pairs: the CTA-per-pair kernel has the lower latency
+    const bool useWarp = nucleotide && (ctx->dpKernel == 2 || (ctx->dpKernel == 0 && n >= ctx->warpMinPairs));
+    if (useWarp) {
+        const int perSm = std::max(1, std::min(ctx->warpCtasPerSm, twl::warpKernelMaxCtasPerSm(matClass)));
+        stages.push_back({3, 32, twl::warpKernelBandCapacity(), std::min(n, ctx->smCount * perSm), tbRows(twl::warpKernelWindow())});
+    }
     if (nucleotide) {
         for (int threads : {128, 256}) {
+            if (useWarp && threads == 128) continue;
             const int cap = twl::wavefrontBandCapacity(threads);
             const int perSm = std::max(1, twl::wavefrontMaxCtasPerSm(threads, matClass));
             stages.push_back({0, threads, cap, std::min(n, ctx->smCount * perSm), tbRows(twl::wavefrontWindow(threads))});
@@ -302,7 +313,8 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
         a.resume = (s > 0) ? 1 : 0;
         a.stateScratch = (st.kind == 2) ? ctx->dState.ptr : nullptr;
         a.stateStride = (st.kind == 2) ? twl::genericStateWords(st.cap) : 0;
-        if (st.kind == 0) TWL_CUDA(ctx, twl::launchTalcoWavefront(st.threads, matClass, a, st.grid, ctx->stream));
+        if (st.kind == 3) TWL_CUDA(ctx, twl::launchTalcoWarp(matClass, a, st.grid, ctx->stream));
+        else if (st.kind == 0) TWL_CUDA(ctx, twl::launchTalcoWavefront(st.threads, matClass, a, st.grid, ctx->stream));
         else TWL_CUDA(ctx, twl::launchTalcoGeneric(ctx->P, st.kind == 2, a, st.grid, st.kind == 1 ? twl::genericStateWords(st.cap) * sizeof(float) : 0, ctx->stream));
         ctx->lastLaunches += 1;
     }
@@ -368,6 +380,9 @@ int twl_align_profiles(twl_ctx *ctx, const twl_profile_pair *pairs, int n_pairs,
 int twl_set_option(twl_ctx *ctx, const char *name, int value) {
     if (!ctx || !name) return TWL_E_ARG;
     if (std::strcmp(name, "force_generic") == 0) { ctx->forceGeneric = value != 0; return TWL_OK; }
+    if (std::strcmp(name, "dp_kernel") == 0) { ctx->dpKernel = value; return TWL_OK; }             // 0 auto, 1 CTA per pair, 2 warp per pair
+    if (std::strcmp(name, "warp_ctas_per_sm") == 0) { ctx->warpCtasPerSm = std::max(1, value); return TWL_OK; }
+    if (std::strcmp(name, "warp_min_pairs") == 0) { ctx->warpMinPairs = std::max(1, value); return TWL_OK; }
     return fail(ctx, TWL_E_ARG, std::string("twl_set_option: unknown option ") + name);
 }
 

@@ -78,6 +78,9 @@ struct twl_ctx {
     DevBuf<uint8_t> dTb;
     DevBuf<float> dState;
 
+    int dpKernel = 1;            // nucleotide first stage: 0 auto, 1 CTA per pair (talco_wavefront.cu), 2 warp per pair (talco_warp.cu)
+    int warpCtasPerSm = 8;
+    int warpMinPairs = 2048;
     bool forceGeneric = false;   // route nucleotide batches through the generic kernel (A/B parity + benchmarking)
     float lastMs = -1.0f;
     int lastLaunches = 0;
