@@ -165,7 +165,9 @@ float twl_last_kernel_ms(const twl_ctx *ctx);
 int twl_last_launch_count(const twl_ctx *ctx);
 
 /* Tuning / diagnostics switches. "force_generic" = 1 routes nucleotide batches through the wide-band generic kernel
- * instead of the register-resident wavefront kernel (results are identical; used by the A/B parity tests). */
+ * instead of the register-resident wavefront kernel (results are identical; used by the A/B parity tests).
+ * "dp_kernel" = 1 (default) one pair per CTA, register-resident wavefront; 2 = experimental one pair per warp
+ * (talco_warp.cu; same results, currently slower); 0 = choose by batch size. "warp_ctas_per_sm", "warp_min_pairs" tune 2/0. */
 int twl_set_option(twl_ctx *ctx, const char *name, int value);
 
 /* Device self-test: evaluates the reciprocal-based exact division used by the DP kernels and the IEEE divide on n

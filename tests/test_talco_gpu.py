@@ -173,3 +173,17 @@ def test_unstructured_matrix_path(which):
         assert o.status == r.error == 0
         assert o.cells == r.cells
         assert np.array_equal(o.path, r.aln_wo), f"pair {k}"
+
+
+def test_warp_per_pair_kernel_matches_port():
+    """The experimental one-pair-per-warp kernel (twl_set_option dp_kernel=2) must produce the same bits."""
+    import twilight_b200
+    cfg, _, _, _, recs = synthetic_records(12, 900, 23, 128)
+    ctx = twilight_b200.Context(marker=128)
+    ctx.set_option("dp_kernel", 2)
+    outs = ctx.align_profiles(records_to_pairs(recs, cfg))
+    ctx.close()
+    for k, (o, r) in enumerate(zip(outs, recs)):
+        assert o.status == r.error == 0
+        assert o.cells == r.cells and o.tiles == r.tiles
+        assert np.array_equal(o.path, r.aln_wo), f"pair {k}"

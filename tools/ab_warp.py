@@ -6,8 +6,7 @@ import bench, twilight_b200
 ids, rows, weights, pairs = bench.build_level_batch(4096, 1500, seed=1000)
 ctx = twilight_b200.Context()
 ref = None
-for name, opts in (("cta", {"dp_kernel": 1}), ("warp x4", {"dp_kernel": 2, "warp_ctas_per_sm": 4}), ("warp x6", {"dp_kernel": 2, "warp_ctas_per_sm": 6}),
-                   ("warp x8", {"dp_kernel": 2, "warp_ctas_per_sm": 8}), ("warp x12", {"dp_kernel": 2, "warp_ctas_per_sm": 12})):
+for name, opts in (("cta", {"dp_kernel": 1}),):
     for k, v in opts.items(): ctx.set_option(k, v)
     for _ in range(3):
         ctx.rows_upload(ids, rows, weights)

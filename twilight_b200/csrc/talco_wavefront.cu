@@ -86,7 +86,7 @@ __device__ __forceinline__ void numerators4(const float (&r)[kSlots][6], const f
 }
 
 template <int NT, int MC>
-__global__ void __launch_bounds__(NT, (NT <= 128 ? 512 / NT : 2)) talcoWavefrontKernel(const TalcoArgs a) {
+__global__ void __launch_bounds__(NT, (NT <= 128 ? 640 / NT : 2)) talcoWavefrontKernel(const TalcoArgs a) {
     constexpr int W = NT * kSlots;
     constexpr int NW = NT / 32;
     constexpr int CW = W + 4;                       // convergence arrays, reference indexing (row - L[k]) plus padding
