@@ -27,11 +27,10 @@
 
 namespace twl {
 
-constexpr int kSlots = 4;
 
 struct WaveShared {
-    int4 red[2][8];            // per warp: (max score as ordered int, first live row, last live row, -)
-    float2 edge[2][8];         // per warp: H and I of the warp's last slot (row-neighbour of the next warp's first slot)
+    int4 red[2][16];            // per warp: (max score as ordered int, first live row, last live row, -)
+    float2 edge[2][16];         // per warp: H and I of the warp's last slot (row-neighbour of the next warp's first slot)
     unsigned convMask[3];
     int8_t ops[2 * kMaxMarker + 16];
     int refOff, qryOff, lastTile, error, nOps, opsBegin, tailLen, tailOp;
@@ -50,12 +49,12 @@ __device__ __forceinline__ void prefetchL1(const void *p) { asm volatile("prefet
 // MC = 1 ("DNA3Z"): the built-in nucleotide matrix shape (scoring-matrix.cpp:103-112 without --wildcard):
 // S[l][l] = A, S[l][m] = B for |l-m| = 2, C otherwise, and an all-zero N row/column. The N terms of the reference sum
 // are exact zeros and are dropped; every remaining product and sum is evaluated in the reference order.
-template <int MC>
-__device__ __forceinline__ void numerators4(const float (&r)[kSlots][6], const float (&q)[kSlots][6], const TalcoArgs &a,
-                                            float (&num)[kSlots]) {
+template <int MC, int KS>
+__device__ __forceinline__ void numerators4(const float (&r)[KS][6], const float (&q)[KS][6], const TalcoArgs &a,
+                                            float (&num)[KS]) {
     if (MC == 0) {
 #pragma unroll
-        for (int c = 0; c < kSlots; ++c) {
+        for (int c = 0; c < KS; ++c) {
             float n = 0.0f;
 #pragma unroll
             for (int l = 0; l < 5; ++l) {
@@ -71,7 +70,7 @@ __device__ __forceinline__ void numerators4(const float (&r)[kSlots][6], const f
     } else {
         const float A = a.scoreNt[0], B = a.scoreNt[2], C = a.scoreNt[1];
 #pragma unroll
-        for (int c = 0; c < kSlots; ++c) {
+        for (int c = 0; c < KS; ++c) {
             float qa[4], qb[4], qc[4];
 #pragma unroll
             for (int m = 0; m < 4; ++m) { qa[m] = __fmul_rn(q[c][m], A); qb[m] = __fmul_rn(q[c][m], B); qc[m] = __fmul_rn(q[c][m], C); }
@@ -85,8 +84,11 @@ __device__ __forceinline__ void numerators4(const float (&r)[kSlots][6], const f
     }
 }
 
-template <int NT, int MC>
-__global__ void __launch_bounds__(NT, (NT <= 128 ? 640 / NT : 2)) talcoWavefrontKernel(const TalcoArgs a) {
+// KS = rows per thread: 4 for throughput (W = 4*NT); 2 with NT = 256 for levels with few pairs, where a CTA runs alone on
+// its SM and the per-thread instruction stream, not the issue rate, sets the time of a diagonal.
+template <int NT, int MC, int KS>
+__global__ void __launch_bounds__(NT, (NT == 96 ? 6 : (NT <= 128 ? 640 / NT : (NT <= 256 ? 2 : 1)))) talcoWavefrontKernel(const TalcoArgs a) {
+    constexpr int kSlots = KS;
     constexpr int W = NT * kSlots;
     constexpr int NW = NT / 32;
     constexpr int CW = W + 4;                       // convergence arrays, reference indexing (row - L[k]) plus padding
@@ -158,7 +160,8 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 640 / NT : 2)) talcoWavefront
 #pragma unroll
                 for (int t = 0; t < 6; ++t) q[c][t] = 0.f;
             }
-            int rowBase = -1;                                          // first of the 4 rows this thread currently holds
+            int rowBase = -1;                                          // first of the rows whose query columns this thread holds
+            int iBase = rho0;                                          // first of the rows this thread computes (= rho0 mod W, >= window base)
             float leftHPrev = -1.0f;                                   // H[k-2] of the row below slot 0
 
             int L0 = 0, U0 = 0, L1 = 2, U1 = -2, L2 = 1, U2 = -1;
@@ -204,7 +207,9 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 640 / NT : 2)) talcoWavefront
                     nbI = (lane == 0) ? e.y : nbI;
                 }
 
-                const int iBase = Lb + ((rho0 - Lb) & (W - 1));         // rows iBase .. iBase+3
+                // rows iBase .. iBase+KS-1: the smallest row >= Lb that is congruent to rho0 mod W. L0 never moves back and
+                // advances by less than W per diagonal (newL <= U0 < Lb + W), so one conditional step keeps it exact for any W.
+                if (iBase < Lb) iBase += W;
                 if (iBase != rowBase) {                                // thread re-assigned: fetch its 4 query columns
                     rowBase = iBase;
 #pragma unroll
@@ -258,8 +263,13 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 640 / NT : 2)) talcoWavefront
                         const long long yOff = 4 * static_cast<long long>(pr.refN4);
 #pragma unroll
                         for (int c = 0; c < kSlots; ++c) {
-                            const int stream = (u - c) & 3;
-                            const int at = stream * pr.refN4 - ((c > u) ? 1 : 0);
+                            long long at;
+                            if (KS == 4) {
+                                const int stream = (u - c) & 3;
+                                at = stream * pr.refN4 - ((c > u) ? 1 : 0);
+                            } else {
+                                at = ntColIndex(m - c, pr.refN4) - (m >> 2);   // rows per thread < 4: the stream differs between threads
+                            }
                             const float4 x = __ldg(pX + at);
                             const float4 y = __ldg(pX + at + yOff);
                             r[c][0] = x.x; r[c][1] = x.y; r[c][2] = x.z; r[c][3] = x.w; r[c][4] = y.x; r[c][5] = y.y;
@@ -290,7 +300,7 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 640 / NT : 2)) talcoWavefront
                             num[c] = __fmaf_rn(r[c][5], gapChar, n);
                         }
                     } else {
-                        numerators4<MC>(r, q, a, num);
+                        numerators4<MC, KS>(r, q, a, num);
                         // gap-character terms (TALCO-XDrop.cpp:393-394): each loop adds exact zeros unless the query (resp.
                         // reference) column holds gaps, so it is skipped when no lane of the warp needs it
                         if (__any_sync(0xffffffffu, gapQ)) {
@@ -375,7 +385,12 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 640 / NT : 2)) talcoWavefront
                         actBits |= (act ? 1u : 0u) << c;
                         tbWord |= (ptr | (insFromIns ? 4u : 0u) | (delFromDel ? 8u : 0u)) << (8 * c);
                     }
-                    if (k <= marker && actBits) *reinterpret_cast<unsigned *>(tb + static_cast<size_t>(k) * W + rho0) = tbWord;
+                    if (k <= marker && actBits) {
+                        uint8_t *dst = tb + static_cast<size_t>(k) * W + rho0;
+                        if (KS == 4) *reinterpret_cast<unsigned *>(dst) = tbWord;
+                        else if (KS == 2) *reinterpret_cast<unsigned short *>(dst) = static_cast<unsigned short>(tbWord);
+                        else *dst = static_cast<uint8_t>(tbWord);
+                    }
                 } else {
 #pragma unroll
                     for (int c = 0; c < kSlots; ++c) h2[c] = h1[c];
@@ -427,14 +442,22 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 640 / NT : 2)) talcoWavefront
                 const int wMax = __reduce_max_sync(0xffffffffu, orderedInt(myMax));
                 const int wLo = __reduce_min_sync(0xffffffffu, myLo);
                 const int wHi = __reduce_max_sync(0xffffffffu, myHi);
-                if (lane == 31) edgeOut[g0 * 8] = make_float2(h1[kSlots - 1], i1[kSlots - 1]);
-                if (lane == 0) redOut[g0 * 8] = make_int4(wMax, wLo, wHi, 0);
+                if (lane == 31) edgeOut[g0 * 16] = make_float2(h1[kSlots - 1], i1[kSlots - 1]);
+                if (lane == 0) redOut[g0 * 16] = make_int4(wMax, wLo, wHi, 0);
                 __syncthreads();
-                int oMax = sh.red[g0][0].x, newL = sh.red[g0][0].y, newU = sh.red[g0][0].z;
+                int oMax, newL, newU;
+                if (NW > 8) {           // many warps: one shared-memory read per lane and three warp reductions
+                    const int4 t = sh.red[g0][lane & (NW - 1)];
+                    oMax = __reduce_max_sync(0xffffffffu, t.x);
+                    newL = __reduce_min_sync(0xffffffffu, t.y);
+                    newU = __reduce_max_sync(0xffffffffu, t.z);
+                } else {
+                    oMax = sh.red[g0][0].x; newL = sh.red[g0][0].y; newU = sh.red[g0][0].z;
 #pragma unroll
-                for (int w = 1; w < NW; ++w) {
-                    const int4 t = sh.red[g0][w];
-                    oMax = max(oMax, t.x); newL = min(newL, t.y); newU = max(newU, t.z);
+                    for (int w = 1; w < NW; ++w) {
+                        const int4 t = sh.red[g0][w];
+                        oMax = max(oMax, t.x); newL = min(newL, t.y); newU = max(newU, t.z);
+                    }
                 }
                 if (newL == 0x7fffffff) { newL = U0 + 1; newU = L0 - 1; }
                 maxScorePrime = fmaxf(maxScorePrime, orderedFloat(oMax));
@@ -510,8 +533,8 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 640 / NT : 2)) talcoWavefront
                     const bool first = (tile == 0);
                     while (kk >= 0 && w > 0) {
                         // the path drifts about half a row per step: pull the line 24 diagonals back into L1 now
-                        if (kk >= 24) prefetchL1(tb + static_cast<size_t>(kk - 24) * W + ((row - 12) & (W - 1)));
-                        const int cell = tb[static_cast<size_t>(kk) * W + (row & (W - 1))];
+                        if (kk >= 24) prefetchL1(tb + static_cast<size_t>(kk - 24) * W + ((row + W - 12) % W));
+                        const int cell = tb[static_cast<size_t>(kk) * W + (row % W)];
                         int dir;
                         if (state == 0) {
                             const int p = cell & 3;
@@ -567,9 +590,9 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 640 / NT : 2)) talcoWavefront
     }
 }
 
-// The wavefront kernels hold bands of up to W-3 cells (the window base is rounded down to a multiple of 4).
-int wavefrontBandCapacity(int threads) { return threads * kSlots - (kSlots - 1); }
-int wavefrontWindow(int threads) { return threads * kSlots; }
+// The wavefront kernels hold bands of up to W-(KS-1) cells (the window base is rounded down to a multiple of KS).
+int wavefrontBandCapacity(int threads, int slots) { return threads * slots - (slots - 1); }
+int wavefrontWindow(int threads, int slots) { return threads * slots; }
 
 // 1 when the matrix has the built-in nucleotide shape with an all-zero N row/column (see numerators4).
 int nucleotideMatrixClass(const float *s) {
@@ -598,28 +621,29 @@ cudaError_t launchDivSelfTest(const float *num, const float *den, int n, int *mi
     return cudaGetLastError();
 }
 
+// supported instantiations: (threads, slots) = (128,4) throughput, (256,4) wide band, (256,2) low latency
 template <int MC>
-static cudaError_t launchMc(int threads, const TalcoArgs &args, int grid, cudaStream_t stream) {
-    switch (threads) {
-    case 64: talcoWavefrontKernel<64, MC><<<grid, 64, 0, stream>>>(args); break;
-    case 128: talcoWavefrontKernel<128, MC><<<grid, 128, 0, stream>>>(args); break;
-    case 256: talcoWavefrontKernel<256, MC><<<grid, 256, 0, stream>>>(args); break;
-    default: return cudaErrorInvalidValue;
-    }
+static cudaError_t launchMc(int threads, int slots, const TalcoArgs &args, int grid, cudaStream_t stream) {
+    if (threads == 128 && slots == 4) talcoWavefrontKernel<128, MC, 4><<<grid, 128, 0, stream>>>(args);
+    else if (threads == 96 && slots == 4) talcoWavefrontKernel<96, MC, 4><<<grid, 96, 0, stream>>>(args);
+    else if (threads == 256 && slots == 4) talcoWavefrontKernel<256, MC, 4><<<grid, 256, 0, stream>>>(args);
+    else if (threads == 256 && slots == 2) talcoWavefrontKernel<256, MC, 2><<<grid, 256, 0, stream>>>(args);
+    else if (threads == 512 && slots == 1) talcoWavefrontKernel<512, MC, 1><<<grid, 512, 0, stream>>>(args);
+    else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
 
-cudaError_t launchTalcoWavefront(int threads, int matClass, const TalcoArgs &args, int grid, cudaStream_t stream) {
-    return matClass == 1 ? launchMc<1>(threads, args, grid, stream) : launchMc<0>(threads, args, grid, stream);
+cudaError_t launchTalcoWavefront(int threads, int slots, int matClass, const TalcoArgs &args, int grid, cudaStream_t stream) {
+    return matClass == 1 ? launchMc<1>(threads, slots, args, grid, stream) : launchMc<0>(threads, slots, args, grid, stream);
 }
 
-int wavefrontMaxCtasPerSm(int threads, int matClass) {
+int wavefrontMaxCtasPerSm(int threads, int slots, int matClass) {
     int n = 0;
-#define TWL_OCC(NT_, MC_) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, talcoWavefrontKernel<NT_, MC_>, NT_, 0)
+#define TWL_OCC(NT_, MC_, KS_) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, talcoWavefrontKernel<NT_, MC_, KS_>, NT_, 0)
     if (matClass == 1) {
-        if (threads == 64) TWL_OCC(64, 1); else if (threads == 128) TWL_OCC(128, 1); else if (threads == 256) TWL_OCC(256, 1);
+        if (threads == 128 && slots == 4) TWL_OCC(128, 1, 4); else if (threads == 96 && slots == 4) TWL_OCC(96, 1, 4); else if (threads == 256 && slots == 4) TWL_OCC(256, 1, 4); else if (threads == 256 && slots == 2) TWL_OCC(256, 1, 2); else if (threads == 512 && slots == 1) TWL_OCC(512, 1, 1);
     } else {
-        if (threads == 64) TWL_OCC(64, 0); else if (threads == 128) TWL_OCC(128, 0); else if (threads == 256) TWL_OCC(256, 0);
+        if (threads == 128 && slots == 4) TWL_OCC(128, 0, 4); else if (threads == 96 && slots == 4) TWL_OCC(96, 0, 4); else if (threads == 256 && slots == 4) TWL_OCC(256, 0, 4); else if (threads == 256 && slots == 2) TWL_OCC(256, 0, 2); else if (threads == 512 && slots == 1) TWL_OCC(512, 0, 1);
     }
 #undef TWL_OCC
     return n;

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -15,11 +16,11 @@ namespace twl {
 size_t genericStateWords(int stateCap);
 cudaError_t launchTalcoGeneric(int P, bool globalState, const TalcoArgs &args, int grid, size_t dynSmemBytes, cudaStream_t stream);
 int genericThreads();
-int wavefrontBandCapacity(int threads);
-int wavefrontWindow(int threads);
+int wavefrontBandCapacity(int threads, int slots);
+int wavefrontWindow(int threads, int slots);
 int nucleotideMatrixClass(const float *score5x5);
-cudaError_t launchTalcoWavefront(int threads, int matClass, const TalcoArgs &args, int grid, cudaStream_t stream);
-int wavefrontMaxCtasPerSm(int threads, int matClass);
+cudaError_t launchTalcoWavefront(int threads, int slots, int matClass, const TalcoArgs &args, int grid, cudaStream_t stream);
+int wavefrontMaxCtasPerSm(int threads, int slots, int matClass);
 int warpKernelBandCapacity();
 int warpKernelWindow();
 cudaError_t launchTalcoWarp(int matClass, const TalcoArgs &args, int grid, cudaStream_t stream);
@@ -113,6 +114,18 @@ int twl_init(int device, twl_ctx **out) {
         cudaEventCreate(&ctx->evStart) != cudaSuccess || cudaEventCreate(&ctx->evStop) != cudaSuccess) {
         delete ctx;
         return fail(nullptr, TWL_E_CUDA, "twl_init: stream/event creation failed");
+    }
+    // tuning switches for A/B runs of unmodified host programs: TWL_OPTIONS="name=value,name=value" (see twl_set_option)
+    if (const char *env = std::getenv("TWL_OPTIONS")) {
+        std::string all(env);
+        size_t at = 0;
+        while (at < all.size()) {
+            const size_t end = std::min(all.find(',', at), all.size());
+            const std::string item = all.substr(at, end - at);
+            const size_t eq = item.find('=');
+            if (eq != std::string::npos) twl_set_option(ctx, item.substr(0, eq).c_str(), std::atoi(item.c_str() + eq + 1));
+            at = end + 1;
+        }
     }
     *out = ctx;
     return TWL_OK;
@@ -249,7 +262,7 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
     const int marker = ctx->marker;
     const int wideCap = std::max(wideCapIn, 8);                     // widest band any pair of the batch may legally reach
     const bool nucleotide = (ctx->P == 6) && !ctx->forceGeneric;
-    struct Stage { int kind; int threads; int cap; int grid; size_t tbStride; };   // kind 0 wavefront (CTA per pair), 1 generic smem, 2 generic global, 3 warp per pair
+    struct Stage { int kind; int threads; int cap; int grid; size_t tbStride; int slots; };   // kind 0 wavefront (CTA per pair), 1 generic smem, 2 generic global, 3 warp per pair
     const int matClass = nucleotide ? twl::nucleotideMatrixClass(ctx->hScore.data()) : 0;
     std::vector<Stage> stages;
     auto tbRows = [&](int w) { return (static_cast<size_t>(marker + 1) * w + 255) & ~static_cast<size_t>(255); };
@@ -257,21 +270,27 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
     const bool useWarp = nucleotide && (ctx->dpKernel == 2 || (ctx->dpKernel == 0 && n >= ctx->warpMinPairs));
     if (useWarp) {
         const int perSm = std::max(1, std::min(ctx->warpCtasPerSm, twl::warpKernelMaxCtasPerSm(matClass)));
-        stages.push_back({3, 32, twl::warpKernelBandCapacity(), std::min(n, ctx->smCount * perSm), tbRows(twl::warpKernelWindow())});
+        stages.push_back({3, 32, twl::warpKernelBandCapacity(), std::min(n, ctx->smCount * perSm), tbRows(twl::warpKernelWindow()), 0});
     }
     if (nucleotide) {
-        for (int threads : {128, 256}) {
-            if (useWarp && threads == 128) continue;
-            const int cap = twl::wavefrontBandCapacity(threads);
-            const int perSm = std::max(1, twl::wavefrontMaxCtasPerSm(threads, matClass));
-            stages.push_back({0, threads, cap, std::min(n, ctx->smCount * perSm), tbRows(twl::wavefrontWindow(threads))});
+        // few pairs (every CTA has an SM to itself): 256 threads x 2 rows shortens the per-thread instruction stream of a
+        // diagonal, which is what bounds a lone CTA; otherwise 128 threads x 4 rows, 5 CTAs per SM
+        const bool lowLatency = !useWarp && ctx->latencyMode != 0 && (ctx->latencyMode == 1 || n <= ctx->smCount);
+        const int first[2] = {lowLatency ? (ctx->latencyShape == 1 ? 512 : 256) : ctx->firstThreads, lowLatency ? (ctx->latencyShape == 1 ? 1 : 2) : 4};
+        const int plan[4][2] = {{first[0], first[1]}, {256, 4}, {0, 0}, {0, 0}};
+        for (int s = 0; plan[s][0]; ++s) {
+            const int threads = plan[s][0], slots = plan[s][1];
+            if (useWarp && s == 0) continue;
+            const int cap = twl::wavefrontBandCapacity(threads, slots);
+            const int perSm = std::max(1, twl::wavefrontMaxCtasPerSm(threads, slots, matClass));
+            stages.push_back({0, threads, cap, std::min(n, ctx->smCount * perSm), tbRows(twl::wavefrontWindow(threads, slots)), slots});
             if (wideCap <= cap) break;
         }
     } else {
         const int cap = std::min(kSmemStateCap, wideCap);
-        stages.push_back({1, twl::genericThreads(), cap, std::min(n, ctx->smCount * kNarrowCtasPerSm), tbBytesPerCta(marker)});
+        stages.push_back({1, twl::genericThreads(), cap, std::min(n, ctx->smCount * kNarrowCtasPerSm), tbBytesPerCta(marker), 0});
     }
-    if (wideCap > stages.back().cap) stages.push_back({2, twl::genericThreads(), wideCap, std::min(n, ctx->smCount), tbBytesPerCta(marker)});
+    if (wideCap > stages.back().cap) stages.push_back({2, twl::genericThreads(), wideCap, std::min(n, ctx->smCount), tbBytesPerCta(marker), 0});
 
     size_t tbBytes = 0, stateWords = 0;
     for (const Stage &st : stages) {
@@ -314,7 +333,7 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
         a.stateScratch = (st.kind == 2) ? ctx->dState.ptr : nullptr;
         a.stateStride = (st.kind == 2) ? twl::genericStateWords(st.cap) : 0;
         if (st.kind == 3) TWL_CUDA(ctx, twl::launchTalcoWarp(matClass, a, st.grid, ctx->stream));
-        else if (st.kind == 0) TWL_CUDA(ctx, twl::launchTalcoWavefront(st.threads, matClass, a, st.grid, ctx->stream));
+        else if (st.kind == 0) TWL_CUDA(ctx, twl::launchTalcoWavefront(st.threads, st.slots, matClass, a, st.grid, ctx->stream));
         else TWL_CUDA(ctx, twl::launchTalcoGeneric(ctx->P, st.kind == 2, a, st.grid, st.kind == 1 ? twl::genericStateWords(st.cap) * sizeof(float) : 0, ctx->stream));
         ctx->lastLaunches += 1;
     }
@@ -380,6 +399,9 @@ int twl_align_profiles(twl_ctx *ctx, const twl_profile_pair *pairs, int n_pairs,
 int twl_set_option(twl_ctx *ctx, const char *name, int value) {
     if (!ctx || !name) return TWL_E_ARG;
     if (std::strcmp(name, "force_generic") == 0) { ctx->forceGeneric = value != 0; return TWL_OK; }
+    if (std::strcmp(name, "first_threads") == 0) { if (value != 96 && value != 128) return TWL_E_ARG; ctx->firstThreads = value; return TWL_OK; }
+    if (std::strcmp(name, "latency_shape") == 0) { ctx->latencyShape = value; return TWL_OK; }   // 0: 256x2, 1: 512x1
+    if (std::strcmp(name, "latency_mode") == 0) { ctx->latencyMode = value; return TWL_OK; }     // -1 auto, 0 off, 1 always
     if (std::strcmp(name, "dp_kernel") == 0) { ctx->dpKernel = value; return TWL_OK; }             // 0 auto, 1 CTA per pair, 2 warp per pair
     if (std::strcmp(name, "warp_ctas_per_sm") == 0) { ctx->warpCtasPerSm = std::max(1, value); return TWL_OK; }
     if (std::strcmp(name, "warp_min_pairs") == 0) { ctx->warpMinPairs = std::max(1, value); return TWL_OK; }
