@@ -629,6 +629,7 @@ static cudaError_t launchMc(int threads, int slots, const TalcoArgs &args, int g
     else if (threads == 256 && slots == 4) talcoWavefrontKernel<256, MC, 4><<<grid, 256, 0, stream>>>(args);
     else if (threads == 256 && slots == 2) talcoWavefrontKernel<256, MC, 2><<<grid, 256, 0, stream>>>(args);
     else if (threads == 512 && slots == 1) talcoWavefrontKernel<512, MC, 1><<<grid, 512, 0, stream>>>(args);
+    else if (threads == 512 && slots == 2) talcoWavefrontKernel<512, MC, 2><<<grid, 512, 0, stream>>>(args);
     else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
@@ -641,9 +642,9 @@ int wavefrontMaxCtasPerSm(int threads, int slots, int matClass) {
     int n = 0;
 #define TWL_OCC(NT_, MC_, KS_) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, talcoWavefrontKernel<NT_, MC_, KS_>, NT_, 0)
     if (matClass == 1) {
-        if (threads == 128 && slots == 4) TWL_OCC(128, 1, 4); else if (threads == 96 && slots == 4) TWL_OCC(96, 1, 4); else if (threads == 256 && slots == 4) TWL_OCC(256, 1, 4); else if (threads == 256 && slots == 2) TWL_OCC(256, 1, 2); else if (threads == 512 && slots == 1) TWL_OCC(512, 1, 1);
+        if (threads == 128 && slots == 4) TWL_OCC(128, 1, 4); else if (threads == 96 && slots == 4) TWL_OCC(96, 1, 4); else if (threads == 256 && slots == 4) TWL_OCC(256, 1, 4); else if (threads == 256 && slots == 2) TWL_OCC(256, 1, 2); else if (threads == 512 && slots == 1) TWL_OCC(512, 1, 1); else if (threads == 512 && slots == 2) TWL_OCC(512, 1, 2);
     } else {
-        if (threads == 128 && slots == 4) TWL_OCC(128, 0, 4); else if (threads == 96 && slots == 4) TWL_OCC(96, 0, 4); else if (threads == 256 && slots == 4) TWL_OCC(256, 0, 4); else if (threads == 256 && slots == 2) TWL_OCC(256, 0, 2); else if (threads == 512 && slots == 1) TWL_OCC(512, 0, 1);
+        if (threads == 128 && slots == 4) TWL_OCC(128, 0, 4); else if (threads == 96 && slots == 4) TWL_OCC(96, 0, 4); else if (threads == 256 && slots == 4) TWL_OCC(256, 0, 4); else if (threads == 256 && slots == 2) TWL_OCC(256, 0, 2); else if (threads == 512 && slots == 1) TWL_OCC(512, 0, 1); else if (threads == 512 && slots == 2) TWL_OCC(512, 0, 2);
     }
 #undef TWL_OCC
     return n;

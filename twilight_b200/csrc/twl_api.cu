@@ -276,8 +276,11 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
         // few pairs (every CTA has an SM to itself): 256 threads x 2 rows shortens the per-thread instruction stream of a
         // diagonal, which is what bounds a lone CTA; otherwise 128 threads x 4 rows, 5 CTAs per SM
         const bool lowLatency = !useWarp && ctx->latencyMode != 0 && (ctx->latencyMode == 1 || n <= ctx->smCount);
-        const int first[2] = {lowLatency ? (ctx->latencyShape == 1 ? 512 : 256) : ctx->firstThreads, lowLatency ? (ctx->latencyShape == 1 ? 1 : 2) : 4};
-        const int plan[4][2] = {{first[0], first[1]}, {256, 4}, {0, 0}, {0, 0}};
+        // latency shapes: 0 = 256x2 then 256x4, 1 = 512x1 then 256x4, 2 = 512x2 (1024-row window at once), 3 = 512x1 then 512x2
+        static const int shapes[4][2][2] = {{{256, 2}, {256, 4}}, {{512, 1}, {256, 4}}, {{512, 2}, {0, 0}}, {{512, 1}, {512, 2}}};
+        const int sh = std::min(std::max(ctx->latencyShape, 0), 3);
+        int plan[4][2] = {{ctx->firstThreads, 4}, {ctx->wideThreads, ctx->wideThreads == 512 ? 2 : 4}, {0, 0}, {0, 0}};
+        if (lowLatency) { plan[0][0] = shapes[sh][0][0]; plan[0][1] = shapes[sh][0][1]; plan[1][0] = shapes[sh][1][0]; plan[1][1] = shapes[sh][1][1]; }
         for (int s = 0; plan[s][0]; ++s) {
             const int threads = plan[s][0], slots = plan[s][1];
             if (useWarp && s == 0) continue;
@@ -336,6 +339,19 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
         else if (st.kind == 0) TWL_CUDA(ctx, twl::launchTalcoWavefront(st.threads, st.slots, matClass, a, st.grid, ctx->stream));
         else TWL_CUDA(ctx, twl::launchTalcoGeneric(ctx->P, st.kind == 2, a, st.grid, st.kind == 1 ? twl::genericStateWords(st.cap) * sizeof(float) : 0, ctx->stream));
         ctx->lastLaunches += 1;
+        if (ctx->dpTrace) {   // diagnosis only: serialises the chain and prints each stage's time and work count
+            static cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if (!e0) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
+            if (s == 0) cudaEventRecord(e0, ctx->stream);   // includes nothing before the first launch's completion
+            cudaEventRecord(e1, ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+            int host[16];
+            cudaMemcpy(host, ctx->dCounters.ptr, sizeof(host), cudaMemcpyDeviceToHost);
+            float ms = 0.f;
+            if (s > 0) cudaEventElapsedTime(&ms, e0, e1);
+            std::fprintf(stderr, "[twl dp] stage %d kind %d %dx%d grid %d: work %d, +%.3f ms since stage 0 ended\n", s, st.kind, st.threads, st.slots, st.grid,
+                         host[2 * s + 1], ms);
+        }
     }
     return TWL_OK;
 }
@@ -400,6 +416,8 @@ int twl_set_option(twl_ctx *ctx, const char *name, int value) {
     if (!ctx || !name) return TWL_E_ARG;
     if (std::strcmp(name, "force_generic") == 0) { ctx->forceGeneric = value != 0; return TWL_OK; }
     if (std::strcmp(name, "first_threads") == 0) { if (value != 96 && value != 128) return TWL_E_ARG; ctx->firstThreads = value; return TWL_OK; }
+    if (std::strcmp(name, "wide_threads") == 0) { if (value != 256 && value != 512) return TWL_E_ARG; ctx->wideThreads = value; return TWL_OK; }
+    if (std::strcmp(name, "dp_trace") == 0) { ctx->dpTrace = value; return TWL_OK; }
     if (std::strcmp(name, "latency_shape") == 0) { ctx->latencyShape = value; return TWL_OK; }   // 0: 256x2, 1: 512x1
     if (std::strcmp(name, "latency_mode") == 0) { ctx->latencyMode = value; return TWL_OK; }     // -1 auto, 0 off, 1 always
     if (std::strcmp(name, "dp_kernel") == 0) { ctx->dpKernel = value; return TWL_OK; }             // 0 auto, 1 CTA per pair, 2 warp per pair
