@@ -159,6 +159,12 @@ int twl_level_fetch(twl_ctx *ctx, int pair, int what, void *dst, size_t cap_byte
  * [2] DP chain, [3] row update + frequency merge. */
 int twl_level_phase_ms(twl_ctx *ctx, float out[4]);
 
+/* addGappyColumnsBack (alignment-helper.cpp:324-375) runs on the device. When removed runs of BOTH nodes start at the same
+ * path position the reference aligns their consensus substrings (pairwiseGlobal, alignment-helper.cpp:243-322); the kernel
+ * keeps that small alignment in shared memory, and a run pair of more than 8192 matrix cells is redone by the library on the
+ * host. Returns how many pairs took that route since twl_init (diagnostics; expected 0 on ordinary data). */
+int twl_level_host_restores(const twl_ctx *ctx);
+
 /* Device time (CUDA events on the context's stream) of the kernels of the last run(), in milliseconds, and the number
  * of kernel launches it issued. */
 float twl_last_kernel_ms(const twl_ctx *ctx);

@@ -127,3 +127,44 @@ def test_level_is_chunked_transparently(monkeypatch):
     ctx.close()
     assert rows_a == rows_b and st_a.cells == st_b.cells and st_a.aln_len == st_b.aln_len
     assert st_b.launches > st_a.launches
+
+
+@pytest.mark.parametrize("ins_len,expect_host", [(25, 0), (150, 1)])
+def test_coinciding_gappy_runs_are_realigned(ins_len, expect_host):
+    """Removed runs of both nodes that start at the same path position are aligned against each other (pairwiseGlobal,
+    alignment-helper.cpp:243-322): in the restore kernel's shared memory when small, by the library's host redo when the
+    matrix exceeds it. Same final path and rows as the oracle either way."""
+    import twilight_b200
+    rng = np.random.default_rng(5)
+    letters = np.frombuffer(b"ACGU", np.uint8)
+    anc = rng.choice(letters, 500)
+
+    def family(seed, members):
+        r = np.random.default_rng(seed)
+        ins = r.choice(letters, ins_len)
+        rows = []
+        for m in range(members):
+            row = anc.copy()
+            flip = r.random(row.size) < 0.03
+            row[flip] = r.choice(letters, int(flip.sum()))
+            mid = ins if m == 0 else np.full(ins_len, ord("-"), np.uint8)     # one member carries an insertion at column 250
+            rows.append(np.concatenate([row[:250], mid, row[250:]]).tobytes())
+        return rows
+
+    ra, rb = family(1, 24), family(2, 24)
+    w = np.ones(48, np.float32)
+    cfg = ol.TalcoCfg()
+    ctx = twilight_b200.Context()
+    ctx.rows_upload(list(range(48)), ra + rb, w)
+    L = len(ra[0])
+    pair = twilight_b200.LevelPairIn(twilight_b200.NodeSideIn(list(range(24)), L, 24, 24.0), twilight_b200.NodeSideIn(list(range(24, 48)), L, 24, 24.0))
+    out = ctx.align_level([pair], task=0, gappy=0.9)[0]
+    sa = ref_msa.NodeState(ra, w[:24], L, 24, 24.0)
+    sb = ref_msa.NodeState(rb, w[24:], L, 24, 24.0)
+    rec = ref_msa.align_pair("n", cfg, sa, sb, 0.9, 0, None, 1000)
+    assert len(rec.runs[0]) >= 1 and len(rec.runs[1]) >= 1          # the case is what it claims to be
+    assert out.status == rec.error == 0
+    assert np.array_equal(out.path, rec.aln_w)
+    assert ctx.rows_download(list(range(48))) == rec.merged.rows
+    assert ctx.host_restores() == expect_host
+    ctx.close()

@@ -264,6 +264,114 @@ __global__ void __launch_bounds__(kLvlThreads) gappyCompactKernel(DevSide *sides
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// addGappyColumnsBack + pairwiseGlobal (src/alignment-helper.cpp:324-375, 243-322). The merge of the removed-column runs
+// back into the DP path is a strictly sequential walk over the path (a run goes in front of the first op at which the
+// original coordinate reaches the run's start; runs hit on both sides at the same op are aligned against each other by a
+// small affine-gap global alignment of the two consensus substrings). One warp per pair, lane 0 walks; the walk costs
+// ~0.1-0.2 ms per pair and thousands of pairs walk concurrently, so the phase is invisible next to the DP.
+// The consensus alignment keeps its matrices in shared memory; a run pair too large for them raises needHost and the
+// library redoes that pair's restore on the host (rare: both runs must be long and start at the same op).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kRestoreTbCells = 8192;       // (m+1)*(n+1) limit of the in-kernel consensus alignment
+constexpr int kRestoreRowCap = 512;         // n+1 limit
+
+__global__ void __launch_bounds__(32) gappyRestoreKernel(DevUpdate *ups, const int *updPair, int nu, const DevPair *pairs, DevResult *results,
+                                                         const DevSide *sides, const int *runs, const char *cons, int8_t *pathsWo,
+                                                         int8_t *finalPaths, const float *score, int M, int isProtein, const signed char *aaLut,
+                                                         float gapOpen, float gapExtend, int *needHost) {
+    __shared__ int8_t tb[kRestoreTbCells];
+    __shared__ float rowM[2][kRestoreRowCap], rowX[2][kRestoreRowCap], rowY[2][kRestoreRowCap];
+    if (threadIdx.x != 0) return;
+    for (int k = blockIdx.x; k < nu; k += gridDim.x) {
+        const int p = updPair[k];
+        DevResult res = results[p];
+        const DevPair pr = pairs[p];
+        const DevSide sr = sides[2 * p], sq = sides[2 * p + 1];
+        int8_t *aln = pathsWo + pr.alnOff;
+        needHost[k] = 0;
+        if (res.status == kStatusEmptySide) {               // alignment-cpu.cpp:89-90: the other side's columns against nothing
+            const int n = (pr.refLen < 1) ? max(pr.qryLen, 0) : max(pr.refLen, 0);
+            const int8_t op = (pr.refLen < 1) ? 1 : 2;
+            for (int a = 0; a < n; ++a) aln[a] = op;
+            res.status = 0; res.pathLen = n;
+            results[p].status = 0; results[p].pathLen = n;
+        }
+        if (res.status != 0) { ups[k].pathLen = 0; continue; }
+        const int alnLen = res.pathLen;
+        const int *runsR = runs + sr.runsOff, *runsQ = runs + sq.runsOff;
+        const int nR = sr.nRuns, nQ = sq.nRuns;
+        const char *consR = cons + sr.consOff, *consQ = cons + sq.consOff;
+        int8_t *out = finalPaths + ups[k].pathOff;
+        int w = 0, r = 0, q = 0, gr = 0, gq = 0;
+        int nextR = (nR > 0) ? runsR[0] : -1, nextQ = (nQ > 0) ? runsQ[0] : -1;
+        bool giveUp = false;
+        for (int a = 0; a <= alnLen; ++a) {
+            const bool hitR = (r == nextR), hitQ = (q == nextQ);
+            if (hitR && hitQ) {
+                const int m = runsR[2 * gr + 1], n = runsQ[2 * gq + 1];
+                if (static_cast<long long>(m + 1) * (n + 1) > kRestoreTbCells || n + 1 > kRestoreRowCap) { giveUp = true; break; }
+                const int W = n + 1;
+                const char *s1 = consR + r, *s2 = consQ + q;
+                for (int j = 0; j <= n; ++j) { rowM[0][j] = 0.0f; rowX[0][j] = (j > 0) ? -1e9f : 0.0f; rowY[0][j] = 0.0f; tb[j] = (j > 0) ? 1 : 0; }
+                for (int i = 1; i <= m; ++i) {
+                    const int cur = i & 1, prv = cur ^ 1;
+                    rowM[cur][0] = 0.0f; rowX[cur][0] = 0.0f; rowY[cur][0] = -1e9f; tb[i * W] = 2;
+                    const unsigned char c1 = static_cast<unsigned char>(s1[i - 1]);
+                    const int l1 = isProtein ? letterIndexAa(c1, aaLut) : letterIndexNt(c1);
+                    for (int j = 1; j <= n; ++j) {
+                        const unsigned char c2 = static_cast<unsigned char>(s2[j - 1]);
+                        const int l2 = isProtein ? letterIndexAa(c2, aaLut) : letterIndexNt(c2);
+                        const float base = score[l1 * M + l2];
+                        const float vm = __fadd_rn(base, fmaxf(fmaxf(rowM[prv][j - 1], rowX[prv][j - 1]), rowY[prv][j - 1]));
+                        const float vx = fmaxf(__fadd_rn(rowM[prv][j], gapOpen), __fadd_rn(rowX[prv][j], gapExtend));
+                        const float vy = fmaxf(__fadd_rn(rowM[cur][j - 1], gapOpen), __fadd_rn(rowY[cur][j - 1], gapExtend));
+                        rowM[cur][j] = vm; rowX[cur][j] = vx; rowY[cur][j] = vy;
+                        const float best = fmaxf(fmaxf(vm, vx), vy);
+                        tb[i * W + j] = (best == vm) ? 0 : ((best == vy) ? 1 : 2);
+                    }
+                }
+                int len = 0;
+                for (int i = m, j = n; i > 0 || j > 0; ++len) {
+                    const int d = tb[i * W + j];
+                    if (d == 0) { --i; --j; } else if (d == 1) { --j; } else { --i; }
+                }
+                int at = w + len;
+                for (int i = m, j = n; i > 0 || j > 0;) {
+                    const int d = tb[i * W + j];
+                    out[--at] = static_cast<int8_t>(d);
+                    if (d == 0) { --i; --j; } else if (d == 1) { --j; } else { --i; }
+                }
+                w += len;
+                ++gr; ++gq; r += m; q += n;
+                nextR = (gr < nR) ? runsR[2 * gr] : -1;
+                nextQ = (gq < nQ) ? runsQ[2 * gq] : -1;
+            } else {
+                if (hitR) {
+                    const int len = runsR[2 * gr + 1];
+                    for (int t = 0; t < len; ++t) out[w + t] = 2;
+                    w += len; r += len; ++gr;
+                    nextR = (gr < nR) ? runsR[2 * gr] : -1;
+                }
+                if (hitQ) {
+                    const int len = runsQ[2 * gq + 1];
+                    for (int t = 0; t < len; ++t) out[w + t] = 1;
+                    w += len; q += len; ++gq;
+                    nextQ = (gq < nQ) ? runsQ[2 * gq] : -1;
+                }
+            }
+            if (a < alnLen) {
+                const int8_t op = aln[a];
+                out[w++] = op;
+                r += (op == 0 || op == 2);
+                q += (op == 0 || op == 1);
+            }
+        }
+        if (giveUp) { needHost[k] = 1; ups[k].pathLen = 0; }
+        else ups[k].pathLen = w;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Per-chunk prefix counts of a final path: chunk c gets (#ref-consuming ops, #qry-consuming ops) in path[0, c*1024).
 // One warp per pair.
 // ---------------------------------------------------------------------------------------------------------------

@@ -26,9 +26,6 @@ struct PairKeep {   // what twl_level_fetch needs from the last level
     long long pathWoOff = -1;
     int pathWoLen = 0;
     std::vector<float> freq[2], merged;
-    std::vector<int32_t> runs[2];
-    std::vector<char> cons[2];
-    std::vector<int8_t> pathWo;
     int chunk = 0;
 };
 
@@ -49,10 +46,16 @@ struct TwlLevelState {
     DevBuf<twl::DevUpdate> dUps;
     DevBuf<int8_t> dFinalPaths;
     DevBuf<signed char> dAaLut;
+    DevBuf<twl::DevUpdate> dUps2;
+    DevBuf<int> dUpdPair, dNeedHost;
+    DevBuf<const char *> dUpdIn;
     PinBuf<twl::DevResult> hRes;
-    PinBuf<int8_t> hPathsWo;
-    PinBuf<int32_t> hRunsPin;
-    PinBuf<char> hConsPin;
+    PinBuf<twl::DevUpdate> hUps;
+    PinBuf<int> hNeedHost;
+    PinBuf<int8_t> hFinal;
+    PinBuf<twl::DevSide> hSides;
+    PinBuf<float> hFreqPin, hMergedPin;
+    int hostRestores = 0;        // pairs whose gappy-column restore fell back to the host since the context was created
     DevBuf<twl::RowCopy> dCopies;
     DevBuf<char> dStage;
     PinBuf<char> hStage;
@@ -188,7 +191,8 @@ void twlLevelDestroy(twl_ctx *ctx) {
     L->dSides.release(); L->dRowIn.release(); L->dRowOut.release(); L->dRowW.release(); L->dRaw.release(); L->dFreq.release();
     L->dMerged.release(); L->dCons.release(); L->dRuns.release(); L->dChunkCounts.release(); L->dUps.release();
     L->dFinalPaths.release(); L->dAaLut.release(); L->dCopies.release(); L->dStage.release(); L->hStage.release();
-    L->hRes.release(); L->hPathsWo.release(); L->hRunsPin.release(); L->hConsPin.release();
+    L->hRes.release(); L->hUps.release(); L->hNeedHost.release(); L->hFinal.release(); L->hSides.release(); L->hFreqPin.release(); L->hMergedPin.release();
+    L->dUps2.release(); L->dUpdPair.release(); L->dNeedHost.release(); L->dUpdIn.release();
     for (auto &e : L->ev) if (e) cudaEventDestroy(e);
     delete L;
     ctx->level = nullptr;
@@ -421,19 +425,93 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
     TWL_CUDA(ctx, cudaMemcpyAsync(ctx->dPairs.ptr, dp.data(), sizeof(DevPair) * n, cudaMemcpyHostToDevice, ctx->stream));
     TWL_CUDA(ctx, cudaMemcpyAsync(ctx->dOrder.ptr, order.data(), sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
 
-    // host-side result buffers are sized before anything is enqueued so the device never waits on the host between phases
+    // ---- the update list is laid out before anything runs, with every path sized by its upper bound (ref + qry columns),
+    // so the whole level — profiles, DP, gappy-column restore, row rewrite — is enqueued without a host round trip
     std::vector<int> work;
     for (int x : order) if (!(pairs[begin + x].flags & TWL_PAIR_PROFILE_ONLY)) work.push_back(x);
+    std::vector<DevUpdate> ups;
+    std::vector<const char *> updIn;
+    std::vector<char *> updOut;
+    std::vector<char> updRegrown;
+    std::vector<int> updPair, upOfPair(n, -1);
+    size_t chunkInts = 0, mergedWords = 0, finalBytes = 0;
+    int maxUb = 0, maxRows = 1;
+    for (int p = 0; p < n; ++p) {
+        const twl_level_pair &in = pairs[begin + p];
+        if (in.flags & TWL_PAIR_PROFILE_ONLY) continue;
+        const DevSide &sr = sides[2 * p], &sq = sides[2 * p + 1];
+        const int ub = in.ref.aln_len + in.qry.aln_len;
+        DevUpdate u;
+        u.pathOff = static_cast<long long>(finalBytes);
+        finalBytes += (static_cast<size_t>(ub) + 16) & ~static_cast<size_t>(15);
+        u.chunkOff = static_cast<long long>(chunkInts);
+        chunkInts += 2 * (static_cast<size_t>(ub + kPathChunk - 1) / kPathChunk + 1);
+        u.memberOff = static_cast<long long>(updIn.size());
+        u.pathLen = 0;                                                       // written by gappyRestoreKernel
+        const bool touchRows = (task != 2) && !(in.flags & TWL_PAIR_NO_ROW_UPDATE);   // currentTask 2 only composes subtree paths (helper.cpp:384)
+        u.nRef = touchRows ? in.ref.n_ids : 0;
+        u.nQry = touchRows ? in.qry.n_ids : 0;
+        u.refWeight = in.ref.aln_weight; u.qryWeight = in.qry.aln_weight; u.pad = 0;
+        const twl_node_side *sd2[2] = {&in.ref, &in.qry};
+        for (int s = 0; s < 2; ++s) {
+            const int cnt = (s == 0) ? u.nRef : u.nQry;
+            for (int m = 0; m < cnt; ++m) {
+                RowSlot &r = L->rows[sd2[s]->seq_ids[m]];
+                updIn.push_back(r.buf[r.storage]);
+                if (r.cap < ub) {                                            // SequenceInfo::memCheck, sequencedb.cpp:57-76
+                    const int cap = 2 * ub;
+                    char *a0, *a1;
+                    TWL_CUDA(ctx, poolAlloc(L, cap, &a0));
+                    TWL_CUDA(ctx, poolAlloc(L, cap, &a1));
+                    // the live buffer keeps being read from its old place for this update; the new pair is used from now on
+                    r.buf[0] = a0; r.buf[1] = a1; r.cap = cap;
+                    updRegrown.push_back(1);
+                } else updRegrown.push_back(0);
+                updOut.push_back(r.buf[1 - r.storage]);
+                r.storage = 1 - r.storage;                                   // changeStorage(); undone below if the pair fails
+            }
+        }
+        // updateFrequency applies when both nodes carry msaFreq after calculateProfile (helper.cpp:508)
+        const bool bothFreq = (sr.freqInOff >= 0 || sr.freqOutOff >= 0) && (sq.freqInOff >= 0 || sq.freqOutOff >= 0);
+        u.freqRefOff = u.freqQryOff = u.mergedOff = -1;
+        if (bothFreq) {
+            u.freqRefOff = (sr.freqInOff >= 0) ? sr.freqInOff : sr.freqOutOff;
+            u.freqQryOff = (sq.freqInOff >= 0) ? sq.freqInOff : sq.freqOutOff;
+            u.mergedOff = static_cast<long long>(mergedWords);
+            mergedWords += static_cast<size_t>(ub) * P;
+        }
+        maxUb = std::max(maxUb, ub);
+        maxRows = std::max(maxRows, u.nRef + u.nQry);
+        upOfPair[p] = static_cast<int>(ups.size());
+        ups.push_back(u);
+        updPair.push_back(p);
+    }
+    const int nu = static_cast<int>(ups.size());
     TWL_CUDA(ctx, L->hRes.reserve(n));
-    TWL_CUDA(ctx, L->hPathsWo.reserve(std::max<size_t>(pathBytes, 16)));
-    TWL_CUDA(ctx, L->hRunsPin.reserve(std::max<size_t>(runInts, 2)));
-    TWL_CUDA(ctx, L->hConsPin.reserve(std::max<size_t>(consBytes, 16)));
+    TWL_CUDA(ctx, L->hUps.reserve(std::max(nu, 1)));
+    TWL_CUDA(ctx, L->hNeedHost.reserve(std::max(nu, 1)));
+    TWL_CUDA(ctx, L->hFinal.reserve(std::max<size_t>(finalBytes, 16)));
+    TWL_CUDA(ctx, L->hSides.reserve(nSides));
+    TWL_CUDA(ctx, L->hFreqPin.reserve(std::max<size_t>(freqWords, 1)));
+    TWL_CUDA(ctx, L->hMergedPin.reserve(std::max<size_t>(mergedWords, 1)));
+    if (nu) {
+        TWL_CUDA(ctx, L->dUps.reserve(nu));
+        TWL_CUDA(ctx, L->dUpdPair.reserve(nu));
+        TWL_CUDA(ctx, L->dNeedHost.reserve(nu));
+        TWL_CUDA(ctx, L->dFinalPaths.reserve(std::max<size_t>(finalBytes, 16)));
+        TWL_CUDA(ctx, L->dChunkCounts.reserve(std::max<size_t>(chunkInts, 2)));
+        TWL_CUDA(ctx, L->dUpdIn.reserve(std::max<size_t>(updIn.size(), 1)));
+        TWL_CUDA(ctx, L->dRowOut.reserve(std::max<size_t>(updOut.size(), 1)));
+        TWL_CUDA(ctx, L->dMerged.reserve(std::max<size_t>(mergedWords, 1)));
+        TWL_CUDA(ctx, cudaMemcpyAsync(L->dUps.ptr, ups.data(), sizeof(DevUpdate) * nu, cudaMemcpyHostToDevice, ctx->stream));
+        TWL_CUDA(ctx, cudaMemcpyAsync(L->dUpdPair.ptr, updPair.data(), sizeof(int) * nu, cudaMemcpyHostToDevice, ctx->stream));
+        if (!updIn.empty()) {
+            TWL_CUDA(ctx, cudaMemcpyAsync(L->dUpdIn.ptr, updIn.data(), sizeof(char *) * updIn.size(), cudaMemcpyHostToDevice, ctx->stream));
+            TWL_CUDA(ctx, cudaMemcpyAsync(L->dRowOut.ptr, updOut.data(), sizeof(char *) * updOut.size(), cudaMemcpyHostToDevice, ctx->stream));
+        }
+    }
     DevResult *res = L->hRes.ptr;
     for (int p = 0; p < n; ++p) { res[p].status = 0; res[p].pathLen = 0; res[p].tiles = 0; res[p].pad = 0; res[p].cells = 0; res[p].diagonals = 0; }
-    int8_t *hostPaths = L->hPathsWo.ptr;
-    int32_t *hRuns = L->hRunsPin.ptr;
-    char *hCons = L->hConsPin.ptr;
-    std::vector<std::vector<int8_t>> finalPath(n);
 
     tr.mark("reserve + H2D description");
     // ---- phase 1: profiles + consensus (+ msaFreq cache); phase 2: gappy-column compaction + PSGP + DP packing
@@ -451,7 +529,8 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
     TWL_CUDA(ctx, cudaEventRecord(L->ev[2], ctx->stream));
     ctx->lastLaunches += 2;
 
-    // ---- phase 3: DP chain (pairs flagged profile-only are simply not listed)
+    // ---- phase 3: DP chain (pairs flagged profile-only are simply not listed). Task 0 reports failed pairs to the caller;
+    // tasks 1 and 2 retry them with wider limits (alignment-cpu.cpp:116-129), which needs the statuses on the host.
     bool first = true;
     while (!work.empty()) {
         const int nw = static_cast<int>(work.size());
@@ -459,211 +538,149 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
         int rc = twlLaunchDpChain(ctx, nw, maxF);
         if (rc != TWL_OK) return rc;
         if (first) TWL_CUDA(ctx, cudaEventRecord(L->ev[3], ctx->stream));
-        TWL_CUDA(ctx, cudaMemcpyAsync(res, ctx->dResults.ptr, sizeof(DevResult) * n, cudaMemcpyDeviceToHost, ctx->stream));
-        TWL_CUDA(ctx, cudaMemcpyAsync(hostPaths, ctx->dPaths.ptr, pathBytes, cudaMemcpyDeviceToHost, ctx->stream));
-        if (first) {
-            TWL_CUDA(ctx, cudaMemcpyAsync(sides.data(), L->dSides.ptr, sizeof(DevSide) * nSides, cudaMemcpyDeviceToHost, ctx->stream));
-            TWL_CUDA(ctx, cudaMemcpyAsync(hRuns, L->dRuns.ptr, sizeof(int32_t) * runInts, cudaMemcpyDeviceToHost, ctx->stream));
-            TWL_CUDA(ctx, cudaMemcpyAsync(hCons, L->dCons.ptr, consBytes, cudaMemcpyDeviceToHost, ctx->stream));
-            TWL_CUDA(ctx, cudaMemcpyAsync(dp.data(), ctx->dPairs.ptr, sizeof(DevPair) * n, cudaMemcpyDeviceToHost, ctx->stream));
-        }
-        TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         first = false;
+        if (task == 0) break;
+        TWL_CUDA(ctx, cudaMemcpyAsync(res, ctx->dResults.ptr, sizeof(DevResult) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        TWL_CUDA(ctx, cudaMemcpyAsync(dp.data(), ctx->dPairs.ptr, sizeof(DevPair) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         std::vector<int> again;
         for (int x : work) {
-            DevResult &r = res[x];
-            if (r.status == kStatusEmptySide) {   // alignment-cpu.cpp:89-90
-                r.status = 0;
-                finalPath[x].clear();
-                std::vector<int8_t> wo;
-                if (dp[x].refLen < 1) wo.assign(std::max(dp[x].qryLen, 0), 1);
-                else wo.assign(std::max(dp[x].refLen, 0), 2);
-                r.pathLen = static_cast<int>(wo.size());
-                std::memcpy(hostPaths + dp[x].alnOff, wo.data(), wo.size());
-            }
-            if (r.status != 0 && task != 0) {     // retry ladder, alignment-cpu.cpp:116-129
-                if (r.status == 3) continue;
-                const int minLen = std::min(dp[x].refLen, dp[x].qryLen);
-                if (r.status == 2) dp[x].fLen = std::min(static_cast<int>(dp[x].fLen * 1.2) << 1, minLen);
-                else { dp[x].xdrop = dp[x].xdrop * 2; dp[x].fLen = std::min(static_cast<int>(dp[x].xdrop * 4) << 1, minLen); }
-                maxF = std::max(maxF, std::min(dp[x].fLen, minLen));
-                again.push_back(x);
-            }
+            const DevResult &r = res[x];
+            if (r.status == 0 || r.status == kStatusEmptySide || r.status == 3) continue;
+            const int minLen = std::min(dp[x].refLen, dp[x].qryLen);
+            if (r.status == 2) dp[x].fLen = std::min(static_cast<int>(dp[x].fLen * 1.2) << 1, minLen);
+            else { dp[x].xdrop = dp[x].xdrop * 2; dp[x].fLen = std::min(static_cast<int>(dp[x].xdrop * 4) << 1, minLen); }
+            maxF = std::max(maxF, std::min(dp[x].fLen, minLen));
+            again.push_back(x);
         }
         if (!again.empty()) TWL_CUDA(ctx, cudaMemcpyAsync(ctx->dPairs.ptr, dp.data(), sizeof(DevPair) * n, cudaMemcpyHostToDevice, ctx->stream));
         work.swap(again);
     }
-    if (first) {   // nothing to align in this chunk: still need the side outputs
-        TWL_CUDA(ctx, cudaEventRecord(L->ev[3], ctx->stream));
-        TWL_CUDA(ctx, cudaMemcpyAsync(sides.data(), L->dSides.ptr, sizeof(DevSide) * nSides, cudaMemcpyDeviceToHost, ctx->stream));
-        TWL_CUDA(ctx, cudaMemcpyAsync(hRuns, L->dRuns.ptr, sizeof(int32_t) * runInts, cudaMemcpyDeviceToHost, ctx->stream));
-        TWL_CUDA(ctx, cudaMemcpyAsync(hCons, L->dCons.ptr, consBytes, cudaMemcpyDeviceToHost, ctx->stream));
-        TWL_CUDA(ctx, cudaMemcpyAsync(dp.data(), ctx->dPairs.ptr, sizeof(DevPair) * n, cudaMemcpyDeviceToHost, ctx->stream));
-        TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    }
+    if (first) TWL_CUDA(ctx, cudaEventRecord(L->ev[3], ctx->stream));   // nothing to align in this chunk
 
-    // ---- host: gappy columns back (helper.cpp:324-375), build the update list
-    tr.mark("kernels + D2H results");
-    // (a) per pair, independent: restore the removed column runs -> final path (host threads)
-    std::vector<char> aligned(n, 0);
-    {
-        auto restoreRange = [&](int t, int nThreads) {
-            for (int p = t; p < n; p += nThreads) {
-                const twl_level_pair &in = pairs[begin + p];
-                twl_level_result &out = results[begin + p];
-                PairKeep &kp = L->keep[begin + p];
-                const DevSide &sr = sides[2 * p], &sq = sides[2 * p + 1];
-                for (int s = 0; s < 2; ++s) {
-                    const DevSide &d = sides[2 * p + s];
-                    kp.newLen[s] = d.newLen; kp.nRuns[s] = d.nRuns;
-                    kp.runs[s].assign(hRuns + d.runsOff, hRuns + d.runsOff + 2 * d.nRuns);
-                    kp.cons[s].assign(hCons + d.consOff, hCons + d.consOff + d.alnLen);
-                }
-                out.status = res[p].status; out.tiles = res[p].tiles; out.cells = res[p].cells; out.diagonals = res[p].diagonals;
-                out.ref_len_dp = sr.newLen; out.qry_len_dp = sq.newLen; out.path_len = 0;
-                out.cached = (sr.freqOutOff >= 0 ? 1 : 0) | (sq.freqOutOff >= 0 ? 2 : 0);
-                if (in.flags & TWL_PAIR_PROFILE_ONLY) { out.status = 0; continue; }
-                if (out.status != 0) continue;
-                kp.pathWo.assign(hostPaths + dp[p].alnOff, hostPaths + dp[p].alnOff + res[p].pathLen);
-                kp.pathWoLen = res[p].pathLen;
-                std::vector<int8_t> &fp = finalPath[p];
-                fp.clear();
-                restoreGappyColumns(type, ctx->hScore, ctx->M, ctx->gapOpen, ctx->gapExtend, kp.pathWo.data(), kp.pathWoLen, kp.runs[0].data(), sr.nRuns,
-                                    kp.runs[1].data(), sq.nRuns, kp.cons[0].data(), kp.cons[1].data(), fp);
-                out.path_len = static_cast<int>(fp.size());
-                if (paths && paths[begin + p]) std::memcpy(paths[begin + p], fp.data(), fp.size());
-                aligned[p] = 1;
-            }
-        };
-        const int nThreads = (n >= 64) ? static_cast<int>(std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()))) : 1;
-        if (nThreads == 1) restoreRange(0, 1);
-        else {
-            std::vector<std::thread> pool;
-            for (int t = 1; t < nThreads; ++t) pool.emplace_back(restoreRange, t, nThreads);
-            restoreRange(0, nThreads);
-            for (auto &th : pool) th.join();
-        }
-    }
-    tr.mark("gappy restore (host threads)");
-    // (b) serial: the update list
-    std::vector<DevUpdate> ups;
-    std::vector<const char *> updIn;
-    std::vector<char *> updOut;
-    std::vector<int8_t> finalStage;
-    std::vector<int> updPair;
-    size_t chunkInts = 0, mergedWords = 0;
-    for (int p = 0; p < n; ++p) {
-        if (!aligned[p]) continue;
-        const twl_level_pair &in = pairs[begin + p];
-        twl_level_result &out = results[begin + p];
-        const DevSide &sr = sides[2 * p], &sq = sides[2 * p + 1];
-        std::vector<int8_t> &fp = finalPath[p];
-
-        DevUpdate u;
-        u.pathOff = static_cast<long long>(finalStage.size());
-        finalStage.insert(finalStage.end(), fp.begin(), fp.end());
-        finalStage.resize((finalStage.size() + 15) & ~static_cast<size_t>(15), 3);
-        u.chunkOff = static_cast<long long>(chunkInts);
-        chunkInts += 2 * ((fp.size() + kPathChunk - 1) / kPathChunk + 1);
-        u.memberOff = static_cast<long long>(updIn.size());
-        u.pathLen = out.path_len;
-        const bool touchRows = (task != 2) && !(in.flags & TWL_PAIR_NO_ROW_UPDATE);   // currentTask 2 only composes subtree paths (helper.cpp:384)
-        u.nRef = touchRows ? in.ref.n_ids : 0;
-        u.nQry = touchRows ? in.qry.n_ids : 0;
-        u.refWeight = in.ref.aln_weight; u.qryWeight = in.qry.aln_weight; u.pad = 0;
-        const twl_node_side *sd2[2] = {&in.ref, &in.qry};
-        for (int s = 0; s < 2; ++s) {
-            const int cnt = (s == 0) ? u.nRef : u.nQry;
-            for (int m = 0; m < cnt; ++m) {
-                RowSlot &r = L->rows[sd2[s]->seq_ids[m]];
-                if (r.cap < out.path_len) {                                 // SequenceInfo::memCheck, sequencedb.cpp:57-76
-                    const int cap = 2 * out.path_len;
-                    char *a0, *a1;
-                    TWL_CUDA(ctx, poolAlloc(L, cap, &a0));
-                    TWL_CUDA(ctx, poolAlloc(L, cap, &a1));
-                    // the live buffer keeps being read from its old place for this update; the new pair is used from now on
-                    updIn.push_back(r.buf[r.storage]);
-                    r.buf[0] = a0; r.buf[1] = a1; r.cap = cap;
-                    updOut.push_back(r.buf[1 - r.storage]);
-                } else {
-                    updIn.push_back(r.buf[r.storage]);
-                    updOut.push_back(r.buf[1 - r.storage]);
-                }
-                r.storage = 1 - r.storage;                                   // changeStorage()
-                r.len = out.path_len;
-            }
-        }
-        // updateFrequency applies when both nodes carry msaFreq after calculateProfile (helper.cpp:508)
-        const bool bothFreq = (sr.freqInOff >= 0 || sr.freqOutOff >= 0) && (sq.freqInOff >= 0 || sq.freqOutOff >= 0);
-        u.freqRefOff = u.freqQryOff = u.mergedOff = -1;
-        if (bothFreq) {
-            u.freqRefOff = (sr.freqInOff >= 0) ? sr.freqInOff : sr.freqOutOff;
-            u.freqQryOff = (sq.freqInOff >= 0) ? sq.freqInOff : sq.freqOutOff;
-            u.mergedOff = static_cast<long long>(mergedWords);
-            mergedWords += static_cast<size_t>(out.path_len) * P;
-            out.cached |= 4;
-        }
-        ups.push_back(u);
-        updPair.push_back(p);
-    }
-
-    tr.mark("build update list (host)");
-    // ---- phase 4: row update + frequency merge
-    bool updateTimed = false;
-    if (!ups.empty()) {
-        const int nu = static_cast<int>(ups.size());
-        int maxPath = 0;
-        for (auto &u : ups) maxPath = std::max(maxPath, u.pathLen);
-        TWL_CUDA(ctx, L->dUps.reserve(nu));
-        TWL_CUDA(ctx, L->dFinalPaths.reserve(std::max<size_t>(finalStage.size(), 16)));
-        TWL_CUDA(ctx, L->dChunkCounts.reserve(std::max<size_t>(chunkInts, 2)));
-        TWL_CUDA(ctx, L->dRowIn.reserve(std::max<size_t>(updIn.size(), 1)));
-        TWL_CUDA(ctx, L->dRowOut.reserve(std::max<size_t>(updOut.size(), 1)));
-        TWL_CUDA(ctx, L->dMerged.reserve(std::max<size_t>(mergedWords, 1)));
-        TWL_CUDA(ctx, cudaMemcpyAsync(L->dUps.ptr, ups.data(), sizeof(DevUpdate) * nu, cudaMemcpyHostToDevice, ctx->stream));
-        TWL_CUDA(ctx, cudaMemcpyAsync(L->dFinalPaths.ptr, finalStage.data(), finalStage.size(), cudaMemcpyHostToDevice, ctx->stream));
-        if (!updIn.empty()) {
-            TWL_CUDA(ctx, cudaMemcpyAsync(L->dRowIn.ptr, updIn.data(), sizeof(char *) * updIn.size(), cudaMemcpyHostToDevice, ctx->stream));
-            TWL_CUDA(ctx, cudaMemcpyAsync(L->dRowOut.ptr, updOut.data(), sizeof(char *) * updOut.size(), cudaMemcpyHostToDevice, ctx->stream));
-        }
-        TWL_CUDA(ctx, cudaEventRecord(L->ev[5], ctx->stream));
-        updateTimed = true;
-        pathChunkKernel<<<(nu * 32 + 255) / 256, 256, 0, ctx->stream>>>(L->dUps.ptr, nu, L->dFinalPaths.ptr, L->dChunkCounts.ptr);
+    // ---- phase 4: gappy columns back (helper.cpp:324-375), row rewrite + frequency merge (helper.cpp:377-448, 506-539)
+    TWL_CUDA(ctx, cudaEventRecord(L->ev[5], ctx->stream));
+    auto launchUpdate = [&](const DevUpdate *dUps, int count, int maxPath, int rowsMax) -> int {
+        pathChunkKernel<<<(count * 32 + 255) / 256, 256, 0, ctx->stream>>>(dUps, count, L->dFinalPaths.ptr, L->dChunkCounts.ptr);
         TWL_CUDA(ctx, cudaGetLastError());
-        int maxRows = 1;
-        for (auto &u : ups) maxRows = std::max(maxRows, u.nRef + u.nQry);
+        const int chunks = std::max(1, (maxPath + kPathChunk - 1) / kPathChunk);
         // enough blocks to fill the GPU when a level has few pairs with many member rows each
-        const int wantZ = std::max(1, (4 * ctx->smCount) / std::max(1, nu * std::max(1, (maxPath + kPathChunk - 1) / kPathChunk)));
-        dim3 grid(nu, std::max(1, (maxPath + kPathChunk - 1) / kPathChunk), std::min(std::min(maxRows, wantZ), 64));
-        rowUpdateKernel<P><<<grid, kLvlThreads, 0, ctx->stream>>>(L->dUps.ptr, L->dFinalPaths.ptr, L->dChunkCounts.ptr, L->dRowIn.ptr, L->dRowOut.ptr,
+        const int wantZ = std::max(1, (4 * ctx->smCount) / std::max(1, count * chunks));
+        dim3 grid(count, chunks, std::min(std::min(rowsMax, wantZ), 64));
+        rowUpdateKernel<P><<<grid, kLvlThreads, 0, ctx->stream>>>(dUps, L->dFinalPaths.ptr, L->dChunkCounts.ptr, L->dUpdIn.ptr, L->dRowOut.ptr,
                                                               L->dFreq.ptr, L->dMerged.ptr);
         TWL_CUDA(ctx, cudaGetLastError());
         ctx->lastLaunches += 2;
+        return TWL_OK;
+    };
+    if (nu) {
+        gappyRestoreKernel<<<std::min(nu, ctx->smCount * 32), 32, 0, ctx->stream>>>(L->dUps.ptr, L->dUpdPair.ptr, nu, ctx->dPairs.ptr, ctx->dResults.ptr,
+                                                                                   L->dSides.ptr, L->dRuns.ptr, L->dCons.ptr, ctx->dPaths.ptr,
+                                                                                   L->dFinalPaths.ptr, ctx->dScore.ptr, ctx->M, P == 6 ? 0 : 1,
+                                                                                   L->dAaLut.ptr, ctx->gapOpen, ctx->gapExtend, L->dNeedHost.ptr);
+        TWL_CUDA(ctx, cudaGetLastError());
+        ctx->lastLaunches += 1;
+        const int rc = launchUpdate(L->dUps.ptr, nu, maxUb, maxRows);
+        if (rc != TWL_OK) return rc;
     }
     TWL_CUDA(ctx, cudaEventRecord(L->ev[4], ctx->stream));
 
-    // ---- msaFreq results back to the host (only nodes >= cache threshold carry them)
-    std::vector<float> hFreq(freqWords), hMerged(mergedWords);
-    if (freqWords) TWL_CUDA(ctx, cudaMemcpyAsync(hFreq.data(), L->dFreq.ptr, sizeof(float) * freqWords, cudaMemcpyDeviceToHost, ctx->stream));
-    if (mergedWords) TWL_CUDA(ctx, cudaMemcpyAsync(hMerged.data(), L->dMerged.ptr, sizeof(float) * mergedWords, cudaMemcpyDeviceToHost, ctx->stream));
+    // ---- results back to the host: one synchronisation per chunk
+    DevSide *hs = L->hSides.ptr;
+    TWL_CUDA(ctx, cudaMemcpyAsync(res, ctx->dResults.ptr, sizeof(DevResult) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    TWL_CUDA(ctx, cudaMemcpyAsync(hs, L->dSides.ptr, sizeof(DevSide) * nSides, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nu) {
+        TWL_CUDA(ctx, cudaMemcpyAsync(L->hUps.ptr, L->dUps.ptr, sizeof(DevUpdate) * nu, cudaMemcpyDeviceToHost, ctx->stream));
+        TWL_CUDA(ctx, cudaMemcpyAsync(L->hNeedHost.ptr, L->dNeedHost.ptr, sizeof(int) * nu, cudaMemcpyDeviceToHost, ctx->stream));
+        if (paths) TWL_CUDA(ctx, cudaMemcpyAsync(L->hFinal.ptr, L->dFinalPaths.ptr, finalBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    float *hFreq = L->hFreqPin.ptr, *hMerged = L->hMergedPin.ptr;
+    if (freqWords) TWL_CUDA(ctx, cudaMemcpyAsync(hFreq, L->dFreq.ptr, sizeof(float) * freqWords, cudaMemcpyDeviceToHost, ctx->stream));
+    if (mergedWords) TWL_CUDA(ctx, cudaMemcpyAsync(hMerged, L->dMerged.ptr, sizeof(float) * mergedWords, cudaMemcpyDeviceToHost, ctx->stream));
     TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    tr.mark("kernels + D2H results");
+
+    // ---- pairs whose consensus alignment did not fit the kernel's shared memory: restore on the host, update again
+    std::vector<int> redo;
+    for (int k = 0; k < nu; ++k) if (L->hNeedHost.ptr[k]) redo.push_back(k);
+    if (!redo.empty()) {
+        std::vector<DevUpdate> again;
+        int maxPath = 0, rowsMax = 1;
+        for (int k : redo) {
+            const int p = updPair[k];
+            const DevSide &sr = hs[2 * p], &sq = hs[2 * p + 1];
+            std::vector<int8_t> wo(std::max(res[p].pathLen, 1)), fp;
+            std::vector<int32_t> rr(2 * std::max(sr.nRuns, 1)), rq(2 * std::max(sq.nRuns, 1));
+            std::vector<char> cr(std::max(sr.alnLen, 1)), cq(std::max(sq.alnLen, 1));
+            TWL_CUDA(ctx, cudaMemcpy(wo.data(), ctx->dPaths.ptr + dp[p].alnOff, res[p].pathLen, cudaMemcpyDeviceToHost));
+            TWL_CUDA(ctx, cudaMemcpy(rr.data(), L->dRuns.ptr + sr.runsOff, sizeof(int32_t) * 2 * sr.nRuns, cudaMemcpyDeviceToHost));
+            TWL_CUDA(ctx, cudaMemcpy(rq.data(), L->dRuns.ptr + sq.runsOff, sizeof(int32_t) * 2 * sq.nRuns, cudaMemcpyDeviceToHost));
+            TWL_CUDA(ctx, cudaMemcpy(cr.data(), L->dCons.ptr + sr.consOff, sr.alnLen, cudaMemcpyDeviceToHost));
+            TWL_CUDA(ctx, cudaMemcpy(cq.data(), L->dCons.ptr + sq.consOff, sq.alnLen, cudaMemcpyDeviceToHost));
+            restoreGappyColumns(type, ctx->hScore, ctx->M, ctx->gapOpen, ctx->gapExtend, wo.data(), res[p].pathLen, rr.data(), sr.nRuns, rq.data(), sq.nRuns,
+                                cr.data(), cq.data(), fp);
+            DevUpdate &u = L->hUps.ptr[k];
+            u.pathLen = static_cast<int>(fp.size());
+            TWL_CUDA(ctx, cudaMemcpy(L->dFinalPaths.ptr + u.pathOff, fp.data(), fp.size(), cudaMemcpyHostToDevice));
+            if (paths) std::memcpy(L->hFinal.ptr + u.pathOff, fp.data(), fp.size());
+            again.push_back(u);
+            maxPath = std::max(maxPath, u.pathLen);
+            rowsMax = std::max(rowsMax, u.nRef + u.nQry);
+        }
+        TWL_CUDA(ctx, L->dUps2.reserve(again.size()));
+        TWL_CUDA(ctx, cudaMemcpyAsync(L->dUps2.ptr, again.data(), sizeof(DevUpdate) * again.size(), cudaMemcpyHostToDevice, ctx->stream));
+        const int rc = launchUpdate(L->dUps2.ptr, static_cast<int>(again.size()), maxPath, rowsMax);
+        if (rc != TWL_OK) return rc;
+        if (mergedWords) TWL_CUDA(ctx, cudaMemcpyAsync(hMerged, L->dMerged.ptr, sizeof(float) * mergedWords, cudaMemcpyDeviceToHost, ctx->stream));
+        TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        L->hostRestores += static_cast<int>(redo.size());
+    }
+
+    // ---- per pair: results, final path, row bookkeeping
     for (int p = 0; p < n; ++p) {
+        const twl_level_pair &in = pairs[begin + p];
+        twl_level_result &out = results[begin + p];
         PairKeep &kp = L->keep[begin + p];
+        const DevSide &sr = hs[2 * p], &sq = hs[2 * p + 1];
         for (int s = 0; s < 2; ++s) {
-            const DevSide &d = sides[2 * p + s];
-            if (d.freqOutOff >= 0) kp.freq[s].assign(hFreq.begin() + d.freqOutOff, hFreq.begin() + d.freqOutOff + static_cast<size_t>(d.alnLen) * P);
+            const DevSide &d = hs[2 * p + s];
+            kp.newLen[s] = d.newLen; kp.nRuns[s] = d.nRuns;
+            if (d.freqOutOff >= 0) kp.freq[s].assign(hFreq + d.freqOutOff, hFreq + d.freqOutOff + static_cast<size_t>(d.alnLen) * P);
+        }
+        out.status = res[p].status; out.tiles = res[p].tiles; out.cells = res[p].cells; out.diagonals = res[p].diagonals;
+        out.ref_len_dp = sr.newLen; out.qry_len_dp = sq.newLen; out.path_len = 0;
+        out.cached = (sr.freqOutOff >= 0 ? 1 : 0) | (sq.freqOutOff >= 0 ? 2 : 0);
+        if (in.flags & TWL_PAIR_PROFILE_ONLY) { out.status = 0; continue; }
+        const int k = upOfPair[p];
+        const DevUpdate &u = L->hUps.ptr[k];
+        kp.pathWoLen = (out.status == 0) ? res[p].pathLen : 0;
+        const twl_node_side *sd2[2] = {&in.ref, &in.qry};
+        long long at = u.memberOff;
+        for (int s = 0; s < 2; ++s) {
+            const int cnt = (s == 0) ? u.nRef : u.nQry;
+            for (int m = 0; m < cnt; ++m, ++at) {
+                RowSlot &r = L->rows[sd2[s]->seq_ids[m]];
+                if (out.status == 0) { r.len = u.pathLen; continue; }
+                r.storage = 1 - r.storage;                                   // the pair failed: the row keeps its old content
+                if (updRegrown[at]) TWL_CUDA(ctx, cudaMemcpyAsync(r.buf[r.storage], updIn[at], r.len, cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+        }
+        if (out.status != 0) continue;
+        out.path_len = u.pathLen;
+        if (paths && paths[begin + p]) std::memcpy(paths[begin + p], L->hFinal.ptr + u.pathOff, static_cast<size_t>(u.pathLen));
+        if (u.mergedOff >= 0) {
+            out.cached |= 4;
+            kp.merged.assign(hMerged + u.mergedOff, hMerged + u.mergedOff + static_cast<size_t>(u.pathLen) * P);
         }
     }
-    for (size_t k = 0; k < ups.size(); ++k)
-        if (ups[k].mergedOff >= 0)
-            L->keep[begin + updPair[k]].merged.assign(hMerged.begin() + ups[k].mergedOff, hMerged.begin() + ups[k].mergedOff + static_cast<size_t>(ups[k].pathLen) * P);
-    tr.mark("update kernels + D2H freq");
+    tr.mark("results to caller (host)");
+    const bool updateTimed = nu > 0;
     for (int i = 0; i < 3; ++i) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, L->ev[i], L->ev[i + 1]);
         L->phaseMs[i] += ms;
     }
-    if (updateTimed) {   // the stream idles between the DP and the update while the host restores gappy columns
+    if (updateTimed) {   // gappy-column restore + path chunk counts + row rewrite / frequency merge
         float ms = 0.f;
         cudaEventElapsedTime(&ms, L->ev[5], L->ev[4]);
         L->phaseMs[3] += ms;
@@ -717,6 +734,8 @@ int twl_align_level(twl_ctx *ctx, const twl_level_pair *pairs, int n_pairs, int 
     return TWL_OK;
 }
 
+int twl_level_host_restores(const twl_ctx *ctx) { return (ctx && ctx->level) ? ctx->level->hostRestores : 0; }
+
 int twl_level_fetch(twl_ctx *ctx, int pair, int what, void *dst, size_t cap_bytes, size_t *out_bytes) {
     if (!ctx || !ctx->level) return TWL_E_ARG;
     TwlLevelState *L = ctx->level;
@@ -754,9 +773,18 @@ int twl_level_fetch(twl_ctx *ctx, int pair, int what, void *dst, size_t cap_byte
         src = tmp.data(); bytes = tmp.size() * sizeof(float);
         break;
     }
-    case TWL_F_CONSENSUS_REF: case TWL_F_CONSENSUS_QRY: src = kp.cons[s].data(); bytes = kp.cons[s].size(); break;
-    case TWL_F_RUNS_REF: case TWL_F_RUNS_QRY: src = kp.runs[s].data(); bytes = kp.runs[s].size() * sizeof(int32_t); break;
-    case TWL_F_PATH_WO: src = kp.pathWo.data(); bytes = kp.pathWo.size(); break;
+    case TWL_F_CONSENSUS_REF: case TWL_F_CONSENSUS_QRY: case TWL_F_RUNS_REF: case TWL_F_RUNS_QRY: case TWL_F_PATH_WO: {
+        // intermediates stay on the device (nothing on the production path reads them); fetched on demand
+        if (kp.chunk != L->lastChunks - 1) return twlFail(ctx, TWL_E_STATE, "twl_level_fetch: intermediates are only kept for the last chunk of a level");
+        const void *dev = nullptr;
+        if (what == TWL_F_PATH_WO) { bytes = static_cast<size_t>(kp.pathWoLen); dev = ctx->dPaths.ptr + kp.pathWoOff; }
+        else if (what == TWL_F_CONSENSUS_REF || what == TWL_F_CONSENSUS_QRY) { bytes = static_cast<size_t>(kp.alnLen[s]); dev = L->dCons.ptr + kp.consOff[s]; }
+        else { bytes = static_cast<size_t>(kp.nRuns[s]) * 2 * sizeof(int32_t); dev = L->dRuns.ptr + kp.runsOff[s]; }
+        tmp.resize((bytes + 3) / 4 + 1);
+        if (bytes) TWL_CUDA(ctx, cudaMemcpy(tmp.data(), dev, bytes, cudaMemcpyDeviceToHost));
+        src = tmp.data();
+        break;
+    }
     case TWL_F_FREQ_REF: src = kp.freq[0].data(); bytes = kp.freq[0].size() * sizeof(float); break;
     case TWL_F_FREQ_QRY: src = kp.freq[1].data(); bytes = kp.freq[1].size() * sizeof(float); break;
     case TWL_F_FREQ_MERGED: src = kp.merged.data(); bytes = kp.merged.size() * sizeof(float); break;
