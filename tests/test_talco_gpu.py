@@ -260,3 +260,31 @@ def test_narrow_window_variant_overflows_to_wide():
         assert out.cells == cells, xdrop
         assert np.array_equal(out.path, want), xdrop
     ctx.close()
+
+
+@pytest.mark.parametrize("workers", [0, 1, 8])
+def test_co_running_wide_workers_match_port(workers):
+    """More pairs than SMs: the narrow kernel and the wide workers run at the same time (twl_set_option wide_workers);
+    pairs whose band outgrows 512 rows are handed over mid-flight. Same bits as the oracle, with and without co-run."""
+    import twilight_b200
+    cfg, _, _, _, recs = synthetic_records(2, 2400, 19, 1024)
+    r = recs[0]
+    pairs, want = [], []
+    for k in range(320):
+        xdrop = (5000, 9000, 14000, 40000)[k % 4] if k % 5 == 0 else 5000
+        key = xdrop
+        pairs.append(twilight_b200.ProfilePairIn(r.profile[0], r.profile[1], r.gap_op[0], r.gap_ex[0], r.gap_op[1], r.gap_ex[1], 1, 1, xdrop=xdrop))
+        want.append(key)
+    oracle = {}
+    for xdrop in set(want):
+        oracle[xdrop] = ol.port_talco(ol.TalcoCfg(xdrop=xdrop), r.profile[0], r.profile[1], r.gap_op[0], r.gap_ex[0], r.gap_op[1], r.gap_ex[1], 1, 1)
+    ctx = twilight_b200.Context(marker=1024)
+    ctx.set_option("wide_workers", workers)
+    for _ in range(2):
+        outs = ctx.align_profiles(pairs)
+        for o, key in zip(outs, want):
+            path, err, cells, tiles, _ = oracle[key]
+            assert o.status == err == 0
+            assert o.cells == cells and o.tiles == tiles
+            assert np.array_equal(o.path, path)
+    ctx.close()

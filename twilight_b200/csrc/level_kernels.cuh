@@ -273,101 +273,177 @@ __global__ void __launch_bounds__(kLvlThreads) gappyCompactKernel(DevSide *sides
 // library redoes that pair's restore on the host (rare: both runs must be long and start at the same op).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kRestoreTbCells = 8192;       // (m+1)*(n+1) limit of the in-kernel consensus alignment
-constexpr int kRestoreRowCap = 512;         // n+1 limit
+constexpr int kRestoreRowCap = 1024;        // n+1 limit
+
+// pairwiseGlobal (alignment-helper.cpp:243-322) of consensus substrings s1[0,m) x s2[0,n) by one warp, row by row: the
+// match and vertical-gap states of a row depend on the previous row only (lanes split the columns), the horizontal-gap
+// state is a running maximum along the row that must be accumulated in the reference's order (lane 0, ~2 dependent
+// instructions per cell). Every cell evaluates exactly the reference's expressions. Writes the ops to out[0, len) and
+// returns len (same value in every lane).
+__device__ __forceinline__ int consensusAlignWarp(int lane, const char *s1, int m, const char *s2, int n, const float *sScore, int M, int isProtein,
+                                                  const signed char *aaLut, float gapOpen, float gapExtend, int8_t *tb,
+                                                  float (*rM)[kRestoreRowCap], float (*rX)[kRestoreRowCap], float (*rY)[kRestoreRowCap],
+                                                  unsigned char *idx2, int8_t *out) {
+    const int W = n + 1;
+    const float big = -1e9f;
+    for (int t = lane; t < n; t += 32) { const unsigned char c = static_cast<unsigned char>(s2[t]); idx2[t] = static_cast<unsigned char>(isProtein ? letterIndexAa(c, aaLut) : letterIndexNt(c)); }
+    for (int j = lane; j <= n; j += 32) { rM[0][j] = 0.0f; rX[0][j] = (j > 0) ? big : 0.0f; rY[0][j] = 0.0f; }
+    __syncwarp();
+    for (int i = 1; i <= m; ++i) {
+        const int cur = i & 1, prv = cur ^ 1;
+        const unsigned char c1 = static_cast<unsigned char>(s1[i - 1]);
+        const float *srow = sScore + (isProtein ? letterIndexAa(c1, aaLut) : letterIndexNt(c1)) * M;
+        for (int j = 1 + lane; j <= n; j += 32) {
+            rM[cur][j] = __fadd_rn(srow[idx2[j - 1]], fmaxf(fmaxf(rM[prv][j - 1], rX[prv][j - 1]), rY[prv][j - 1]));
+            rX[cur][j] = fmaxf(__fadd_rn(rM[prv][j], gapOpen), __fadd_rn(rX[prv][j], gapExtend));
+        }
+        if (lane == 0) { rM[cur][0] = 0.0f; rX[cur][0] = 0.0f; rY[cur][0] = big; }
+        __syncwarp();
+        if (lane == 0) {
+            float y = big;
+#pragma unroll 4
+            for (int j = 1; j <= n; ++j) {
+                y = fmaxf(__fadd_rn(rM[cur][j - 1], gapOpen), __fadd_rn(y, gapExtend));
+                rY[cur][j] = y;
+            }
+        }
+        __syncwarp();
+        for (int j = 1 + lane; j <= n; j += 32) {
+            const float vm = rM[cur][j], vx = rX[cur][j], vy = rY[cur][j];
+            const float best = fmaxf(fmaxf(vm, vx), vy);
+            tb[i * W + j] = (best == vm) ? 0 : ((best == vy) ? 1 : 2);
+        }
+    }
+    __syncwarp();
+    int len = 0;
+    if (lane == 0) {
+        for (int i = m, j = n; i > 0 || j > 0; ++len) {
+            const int d = (i == 0) ? 1 : ((j == 0) ? 2 : tb[i * W + j]);
+            if (d == 0) { --i; --j; } else if (d == 1) { --j; } else { --i; }
+        }
+        int at = len;
+        for (int i = m, j = n; i > 0 || j > 0;) {
+            const int d = (i == 0) ? 1 : ((j == 0) ? 2 : tb[i * W + j]);
+            out[--at] = static_cast<int8_t>(d);
+            if (d == 0) { --i; --j; } else if (d == 1) { --j; } else { --i; }
+        }
+    }
+    __syncwarp();
+    return __shfl_sync(0xffffffffu, len, 0);
+}
 
 __global__ void __launch_bounds__(32) gappyRestoreKernel(DevUpdate *ups, const int *updPair, int nu, const DevPair *pairs, DevResult *results,
                                                          const DevSide *sides, const int *runs, const char *cons, int8_t *pathsWo,
                                                          int8_t *finalPaths, const float *score, int M, int isProtein, const signed char *aaLut,
                                                          float gapOpen, float gapExtend, int *needHost) {
     __shared__ int8_t tb[kRestoreTbCells];
-    __shared__ float rowM[2][kRestoreRowCap], rowX[2][kRestoreRowCap], rowY[2][kRestoreRowCap];
-    if (threadIdx.x != 0) return;
+    __shared__ float dM[2][kRestoreRowCap], dX[2][kRestoreRowCap], dY[2][kRestoreRowCap];
+    // staged windows of the two run lists and of the path: the walk is a chain of dependent reads, which must not each
+    // pay a trip to L2
+    constexpr int kRunWin = 256, kOpWin = 1024;
+    __shared__ int sRunR[2 * kRunWin], sRunQ[2 * kRunWin];
+    __shared__ __align__(16) int8_t sOps[kOpWin];
+    __shared__ unsigned char sIdx2[kRestoreRowCap];
+    __shared__ float sScore[21 * 21];
+    const int lane = threadIdx.x;
+    for (int t = lane; t < M * M; t += 32) sScore[t] = score[t];
+    __syncwarp();
+    // every lane keeps the (uniform) walk state; lane-parallel parts: op copies, run fills, the consensus alignment
     for (int k = blockIdx.x; k < nu; k += gridDim.x) {
         const int p = updPair[k];
         DevResult res = results[p];
         const DevPair pr = pairs[p];
         const DevSide sr = sides[2 * p], sq = sides[2 * p + 1];
         int8_t *aln = pathsWo + pr.alnOff;
-        needHost[k] = 0;
+        __syncwarp();
+        if (lane == 0) needHost[k] = 0;
         if (res.status == kStatusEmptySide) {               // alignment-cpu.cpp:89-90: the other side's columns against nothing
             const int n = (pr.refLen < 1) ? max(pr.qryLen, 0) : max(pr.refLen, 0);
             const int8_t op = (pr.refLen < 1) ? 1 : 2;
-            for (int a = 0; a < n; ++a) aln[a] = op;
+            for (int a = lane; a < n; a += 32) aln[a] = op;
             res.status = 0; res.pathLen = n;
-            results[p].status = 0; results[p].pathLen = n;
+            if (lane == 0) { results[p].status = 0; results[p].pathLen = n; }
+            __syncwarp();
         }
-        if (res.status != 0) { ups[k].pathLen = 0; continue; }
+        if (res.status != 0) { if (lane == 0) ups[k].pathLen = 0; continue; }
         const int alnLen = res.pathLen;
         const int *runsR = runs + sr.runsOff, *runsQ = runs + sq.runsOff;
         const int nR = sr.nRuns, nQ = sq.nRuns;
         const char *consR = cons + sr.consOff, *consQ = cons + sq.consOff;
         int8_t *out = finalPaths + ups[k].pathOff;
-        int w = 0, r = 0, q = 0, gr = 0, gq = 0;
-        int nextR = (nR > 0) ? runsR[0] : -1, nextQ = (nQ > 0) ? runsQ[0] : -1;
+        int baseR = 0, baseQ = 0, baseA = 0;
+        auto stageRuns = [&](const int *src, int *dst, int base, int total) {
+            __syncwarp();
+            const int cnt = 2 * min(kRunWin, total - base);
+            for (int t = lane; t < cnt; t += 32) dst[t] = src[2 * base + t];
+            __syncwarp();
+        };
+        auto stageOps = [&](int base) {          // base is a multiple of 16; the path buffer is padded to 16 bytes
+            __syncwarp();
+            const int cnt = min(kOpWin, ((alnLen - base) + 15) & ~15);
+            for (int t = lane * 16; t < cnt; t += 32 * 16)
+                *reinterpret_cast<uint4 *>(sOps + t) = *reinterpret_cast<const uint4 *>(aln + base + t);
+            __syncwarp();
+        };
+        stageRuns(runsR, sRunR, 0, nR);
+        stageRuns(runsQ, sRunQ, 0, nQ);
+        stageOps(0);
+        int w = 0, r = 0, q = 0, gr = 0, gq = 0, a = 0;
+        int nextR = (nR > 0) ? sRunR[0] : -1, nextQ = (nQ > 0) ? sRunQ[0] : -1;
         bool giveUp = false;
-        for (int a = 0; a <= alnLen; ++a) {
+        for (;;) {
+            // runs that start at the current original coordinates go in front of op a (helper.cpp:338-362)
             const bool hitR = (r == nextR), hitQ = (q == nextQ);
             if (hitR && hitQ) {
-                const int m = runsR[2 * gr + 1], n = runsQ[2 * gq + 1];
+                const int m = sRunR[2 * (gr - baseR) + 1], n = sRunQ[2 * (gq - baseQ) + 1];
                 if (static_cast<long long>(m + 1) * (n + 1) > kRestoreTbCells || n + 1 > kRestoreRowCap) { giveUp = true; break; }
-                const int W = n + 1;
-                const char *s1 = consR + r, *s2 = consQ + q;
-                for (int j = 0; j <= n; ++j) { rowM[0][j] = 0.0f; rowX[0][j] = (j > 0) ? -1e9f : 0.0f; rowY[0][j] = 0.0f; tb[j] = (j > 0) ? 1 : 0; }
-                for (int i = 1; i <= m; ++i) {
-                    const int cur = i & 1, prv = cur ^ 1;
-                    rowM[cur][0] = 0.0f; rowX[cur][0] = 0.0f; rowY[cur][0] = -1e9f; tb[i * W] = 2;
-                    const unsigned char c1 = static_cast<unsigned char>(s1[i - 1]);
-                    const int l1 = isProtein ? letterIndexAa(c1, aaLut) : letterIndexNt(c1);
-                    for (int j = 1; j <= n; ++j) {
-                        const unsigned char c2 = static_cast<unsigned char>(s2[j - 1]);
-                        const int l2 = isProtein ? letterIndexAa(c2, aaLut) : letterIndexNt(c2);
-                        const float base = score[l1 * M + l2];
-                        const float vm = __fadd_rn(base, fmaxf(fmaxf(rowM[prv][j - 1], rowX[prv][j - 1]), rowY[prv][j - 1]));
-                        const float vx = fmaxf(__fadd_rn(rowM[prv][j], gapOpen), __fadd_rn(rowX[prv][j], gapExtend));
-                        const float vy = fmaxf(__fadd_rn(rowM[cur][j - 1], gapOpen), __fadd_rn(rowY[cur][j - 1], gapExtend));
-                        rowM[cur][j] = vm; rowX[cur][j] = vx; rowY[cur][j] = vy;
-                        const float best = fmaxf(fmaxf(vm, vx), vy);
-                        tb[i * W + j] = (best == vm) ? 0 : ((best == vy) ? 1 : 2);
-                    }
-                }
-                int len = 0;
-                for (int i = m, j = n; i > 0 || j > 0; ++len) {
-                    const int d = tb[i * W + j];
-                    if (d == 0) { --i; --j; } else if (d == 1) { --j; } else { --i; }
-                }
-                int at = w + len;
-                for (int i = m, j = n; i > 0 || j > 0;) {
-                    const int d = tb[i * W + j];
-                    out[--at] = static_cast<int8_t>(d);
-                    if (d == 0) { --i; --j; } else if (d == 1) { --j; } else { --i; }
-                }
-                w += len;
-                ++gr; ++gq; r += m; q += n;
-                nextR = (gr < nR) ? runsR[2 * gr] : -1;
-                nextQ = (gq < nQ) ? runsQ[2 * gq] : -1;
+                w += consensusAlignWarp(lane, consR + r, m, consQ + q, n, sScore, M, isProtein, aaLut, gapOpen, gapExtend, tb, dM, dX, dY, sIdx2, out + w);
+                r += m; q += n;
             } else {
                 if (hitR) {
-                    const int len = runsR[2 * gr + 1];
-                    for (int t = 0; t < len; ++t) out[w + t] = 2;
-                    w += len; r += len; ++gr;
-                    nextR = (gr < nR) ? runsR[2 * gr] : -1;
+                    const int len = sRunR[2 * (gr - baseR) + 1];
+                    for (int t = lane; t < len; t += 32) out[w + t] = 2;
+                    w += len; r += len;
                 }
                 if (hitQ) {
-                    const int len = runsQ[2 * gq + 1];
-                    for (int t = 0; t < len; ++t) out[w + t] = 1;
-                    w += len; q += len; ++gq;
-                    nextQ = (gq < nQ) ? runsQ[2 * gq] : -1;
+                    const int len = sRunQ[2 * (gq - baseQ) + 1];
+                    for (int t = lane; t < len; t += 32) out[w + t] = 1;
+                    w += len; q += len;
                 }
             }
-            if (a < alnLen) {
-                const int8_t op = aln[a];
-                out[w++] = op;
-                r += (op == 0 || op == 2);
-                q += (op == 0 || op == 1);
+            if (hitR) {
+                ++gr;
+                if (gr < nR && gr >= baseR + kRunWin) { baseR = gr; stageRuns(runsR, sRunR, baseR, nR); }
+                nextR = (gr < nR) ? sRunR[2 * (gr - baseR)] : -1;
             }
+            if (hitQ) {
+                ++gq;
+                if (gq < nQ && gq >= baseQ + kRunWin) { baseQ = gq; stageRuns(runsQ, sRunQ, baseQ, nQ); }
+                nextQ = (gq < nQ) ? sRunQ[2 * (gq - baseQ)] : -1;
+            }
+            if (a >= alnLen) break;
+            // copy ops a, a+1, ... up to (not including) the first later op in front of which a run starts
+            const int left = min(32, alnLen - a);
+            if (a + left > baseA + kOpWin) { baseA = a & ~15; stageOps(baseA); }
+            const int op = (lane < left) ? sOps[a - baseA + lane] : 3;
+            // a run goes in front of the first op at which the number of consumed columns reaches its start
+            const unsigned maskR = __ballot_sync(0xffffffffu, op == 0 || op == 2);
+            const unsigned maskQ = __ballot_sync(0xffffffffu, op == 0 || op == 1);
+            const unsigned below = (1u << lane) - 1u;
+            const bool hitHere = (lane > 0) && (lane < left) && ((r + __popc(maskR & below) == nextR) || (q + __popc(maskQ & below) == nextQ));
+            const unsigned hits = __ballot_sync(0xffffffffu, hitHere);
+            const int take = hits ? (__ffs(hits) - 1) : left;      // >= 1
+            if (lane < take) out[w + lane] = static_cast<int8_t>(op);
+            const unsigned upto = (take >= 32) ? 0xffffffffu : ((1u << take) - 1u);
+            r += __popc(maskR & upto);
+            q += __popc(maskQ & upto);
+            w += take; a += take;
         }
-        if (giveUp) { needHost[k] = 1; ups[k].pathLen = 0; }
-        else ups[k].pathLen = w;
+        __syncwarp();
+        if (lane == 0) {
+            if (giveUp) { needHost[k] = 1; ups[k].pathLen = 0; }
+            else ups[k].pathLen = w;
+        }
     }
 }
 

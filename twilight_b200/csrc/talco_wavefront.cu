@@ -34,9 +34,10 @@ struct WaveShared {
     unsigned convMask[3];
     int8_t ops[2 * kMaxMarker + 16];
     int refOff, qryOff, lastTile, error, nOps, opsBegin, tailLen, tailOp;
-    int work;
+    int work, fed;
 };
 
+__device__ __forceinline__ unsigned long long globalTimerNs() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ int orderedInt(float f) {
     const int b = __float_as_int(f);
     return b ^ ((b >> 31) & 0x7fffffff);
@@ -102,17 +103,50 @@ __global__ void __launch_bounds__(NT, (NT == 96 ? 6 : (NT <= 128 ? 640 / NT : (N
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) sh.work = atomicAdd(a.queue, 1);
+        if (tid == 0) {
+            if (a.coMode == 2) {
+                // wide worker: fed pairs first, then the main queue; leave when every main pair is finished and nothing is fed
+                const int nMain = *a.nWorkPtr;
+                int got = -1, fed = 0;
+                for (;;) {
+                    const int cur = *reinterpret_cast<volatile int *>(a.feedCursor);
+                    if (cur < *reinterpret_cast<volatile int *>(a.feedCount)) {
+                        if (atomicCAS(a.feedCursor, cur, cur + 1) == cur) {
+                            int e;
+                            while ((e = *reinterpret_cast<volatile int *>(a.feedList + cur)) < 0) __nanosleep(64);
+                            __threadfence();
+                            got = e; fed = 1;
+                            if (a.coTrace) a.coTrace[4 * e + 1] = globalTimerNs();
+                            break;
+                        }
+                        continue;
+                    }
+                    if (*reinterpret_cast<volatile int *>(a.queue) < a.coTakeBelow) {
+                        const int w = atomicAdd(a.queue, 1);
+                        if (w < nMain) { got = a.order[w]; break; }
+                    }
+                    if (*reinterpret_cast<volatile int *>(a.mainDone) >= nMain &&
+                        *reinterpret_cast<volatile int *>(a.feedCursor) >= *reinterpret_cast<volatile int *>(a.feedCount)) break;
+                    __nanosleep(256);
+                }
+                sh.work = got; sh.fed = fed;
+            } else {
+                const int w = atomicAdd(a.queue, 1);
+                sh.work = (w < *a.nWorkPtr) ? a.order[w] : -1;
+                sh.fed = 0;
+            }
+        }
         __syncthreads();
-        const int work = sh.work;
-        if (work >= *a.nWorkPtr) break;
-        const int pairIdx = a.order[work];
+        const int pairIdx = sh.work;
+        if (pairIdx < 0) break;
+        const bool fedPair = sh.fed != 0;
         const DevPair pr = a.pairs[pairIdx];
         if (pr.refLen < 1 || pr.qryLen < 1) {   // an empty side (after gappy-column removal): nothing to align, the host emits the trivial path
             if (tid == 0) {
                 DevResult res;
                 res.status = kStatusEmptySide; res.pathLen = 0; res.tiles = 0; res.pad = 0; res.cells = 0; res.diagonals = 0; res.resRefOff = 0; res.resQryOff = 0;
                 a.results[pairIdx] = res;
+                if (a.coMode && !fedPair) { __threadfence(); atomicAdd(a.mainDone, 1); }
             }
             continue;
         }
@@ -131,8 +165,15 @@ __global__ void __launch_bounds__(NT, (NT == 96 ? 6 : (NT <= 128 ? 640 / NT : (N
         int refOff = 0, qryOff = 0, tile = 0, outPos = 0, status = 0;
         unsigned long long cells = 0, diagonals = 0;
         bool lastTile = false;
-        if (a.resume) {   // the previous kernel of the chain finished some tiles of this pair before its band capacity ran out
-            const DevResult prev = a.results[pairIdx];
+        if (a.resume || fedPair) {   // another kernel finished some tiles of this pair before its band capacity ran out
+            DevResult prev;   // read around L1: the entry may have been written by a CTA of the co-running kernel a moment ago
+            {
+                static_assert(sizeof(DevResult) == 40, "DevResult layout");
+                const unsigned long long *src = reinterpret_cast<const unsigned long long *>(a.results + pairIdx);
+                unsigned long long *dst = reinterpret_cast<unsigned long long *>(&prev);
+#pragma unroll
+                for (int t = 0; t < 5; ++t) dst[t] = __ldcg(src + t);
+            }
             if (prev.status == kStatusRetryWide) {
                 refOff = prev.resRefOff; qryOff = prev.resQryOff; tile = prev.tiles; outPos = prev.pathLen;
                 cells = prev.cells; diagonals = prev.diagonals;
@@ -575,7 +616,6 @@ __global__ void __launch_bounds__(NT, (NT == 96 ? 6 : (NT <= 128 ? 640 / NT : (N
         }
 
         if (tid == 0) {
-            if (status == kStatusRetryWide && a.overflowList != nullptr) a.overflowList[atomicAdd(a.overflowCount, 1)] = pairIdx;
             DevResult res;
             res.status = status;
             res.pathLen = status ? 0 : outPos;
@@ -586,8 +626,19 @@ __global__ void __launch_bounds__(NT, (NT == 96 ? 6 : (NT <= 128 ? 640 / NT : (N
             res.resRefOff = refOff; res.resQryOff = qryOff;
             if (status == kStatusRetryWide) { res.pathLen = outPos; }
             a.results[pairIdx] = res;
+            if (status == kStatusRetryWide) {
+                if (a.coMode == 1) {   // hand the pair to the co-running wide workers: result and partial path first, then the entry
+                    __threadfence();
+                    if (a.coTrace) a.coTrace[4 * pairIdx + 0] = globalTimerNs();
+                    const int slot = atomicAdd(a.feedCount, 1);
+                    atomicExch(a.feedList + slot, pairIdx);
+                } else if (a.overflowList != nullptr) a.overflowList[atomicAdd(a.overflowCount, 1)] = pairIdx;
+            }
+            if (a.coMode && !fedPair) { __threadfence(); atomicAdd(a.mainDone, 1); }
+            if (a.coTrace && a.coMode == 2) { a.coTrace[4 * pairIdx + 2] = globalTimerNs(); a.coTrace[4 * pairIdx + 3] = fedPair ? 2 : 1; }
         }
     }
+    if (a.coTrace && tid == 0 && blockIdx.x == 0) a.coTrace[4 * (*a.nWorkPtr) + (a.coMode == 2 ? 1 : 0)] = globalTimerNs();
 }
 
 // The wavefront kernels hold bands of up to W-(KS-1) cells (the window base is rounded down to a multiple of KS).

@@ -140,6 +140,9 @@ void twl_destroy(twl_ctx *ctx) {
     ctx->hProf.release(); ctx->hPaths.release(); ctx->hResults.release();
     if (ctx->evStart) cudaEventDestroy(ctx->evStart);
     if (ctx->evStop) cudaEventDestroy(ctx->evStop);
+    if (ctx->evFork) cudaEventDestroy(ctx->evFork);
+    if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
     twlLevelDestroy(ctx);
     delete ctx;
@@ -295,21 +298,44 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
     }
     if (wideCap > stages.back().cap) stages.push_back({2, twl::genericThreads(), wideCap, std::min(n, ctx->smCount), tbBytesPerCta(marker), 0});
 
+    // Co-run: stage 0 (narrow window, 5 CTAs per SM) and stage 1 (wide window) execute at the same time; see TalcoArgs::coMode.
+    const bool coRun = nucleotide && !useWarp && ctx->wideWorkers > 0 && stages.size() >= 2 && stages[0].kind == 0 && stages[1].kind == 0 &&
+                       stages[1].cap > stages[0].cap && n > ctx->smCount;
+    int wideGrid = 0;
+    bool takeMain = false;
+    if (coRun) {
+        const int perSm = std::max(1, twl::wavefrontMaxCtasPerSm(stages[0].threads, stages[0].slots, matClass));
+        // Many pairs per narrow CTA slot: a few wide workers that also eat from the main queue. About one wave or less: the
+        // wide workers take the SMs the narrow kernel does not need and only serve handed-over pairs, which then restart at once.
+        takeMain = n > ctx->smCount * perSm;
+        if (takeMain) wideGrid = std::min(ctx->wideWorkers, ctx->smCount / 4);
+        else wideGrid = std::min(ctx->smCount / 4, std::max(ctx->wideWorkers, (ctx->smCount * perSm - n) / perSm));
+        stages[1].grid = wideGrid;
+        stages[0].grid = std::min(n, (ctx->smCount - wideGrid) * perSm);
+        if (!ctx->stream2) {
+            TWL_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+            TWL_CUDA(ctx, cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming));
+            TWL_CUDA(ctx, cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming));
+        }
+    }
     size_t tbBytes = 0, stateWords = 0;
     for (const Stage &st : stages) {
         tbBytes = std::max(tbBytes, st.tbStride * static_cast<size_t>(st.grid));
         if (st.kind == 2) stateWords = twl::genericStateWords(st.cap) * static_cast<size_t>(st.grid);
     }
+    const size_t tbNarrow = coRun ? stages[0].tbStride * static_cast<size_t>(stages[0].grid) : 0;
+    if (coRun) tbBytes = std::max(tbBytes, tbNarrow + stages[1].tbStride * static_cast<size_t>(stages[1].grid));
     TWL_CUDA(ctx, ctx->dTb.reserve(tbBytes));
     if (stateWords) TWL_CUDA(ctx, ctx->dState.reserve(stateWords));
     const int nStages = static_cast<int>(stages.size());
     TWL_CUDA(ctx, ctx->dOverflow.reserve(static_cast<size_t>(n) * std::max(1, nStages - 1)));
 
-    // counters: [2*s] = queue cursor of stage s, [2*s+1] = work count of stage s
+    // counters: [2*s] = queue cursor of stage s, [2*s+1] = work count of stage s; co-run: [2] feed cursor, [3] feed count, [14] main pairs finished
     int counters[16] = {0};
     counters[1] = n;
     TWL_CUDA(ctx, ctx->dCounters.reserve(16));
     TWL_CUDA(ctx, cudaMemcpyAsync(ctx->dCounters.ptr, counters, sizeof(counters), cudaMemcpyHostToDevice, ctx->stream));
+    if (coRun) TWL_CUDA(ctx, cudaMemsetAsync(ctx->dOverflow.ptr, 0xFF, sizeof(int) * static_cast<size_t>(n), ctx->stream));
 
     twl::TalcoArgs a{};
     a.prof = ctx->dProf.ptr + kProfPadWords;
@@ -330,11 +356,66 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
         a.nWorkPtr = ctx->dCounters.ptr + 2 * s + 1;
         a.overflowList = hasNext ? ctx->dOverflow.ptr + static_cast<size_t>(n) * s : nullptr;
         a.overflowCount = hasNext ? ctx->dCounters.ptr + 2 * (s + 1) + 1 : nullptr;
+        a.tbScratch = ctx->dTb.ptr;
         a.tbStride = st.tbStride;
         a.stateCap = st.cap;
         a.resume = (s > 0) ? 1 : 0;
         a.stateScratch = (st.kind == 2) ? ctx->dState.ptr : nullptr;
         a.stateStride = (st.kind == 2) ? twl::genericStateWords(st.cap) : 0;
+        a.coMode = 0;
+        if (coRun && s == 0) {
+            // the wide workers go first so that they hold their SMs before the narrow CTAs fill the machine
+            twl::TalcoArgs w = a;
+            const Stage &sw = stages[1];
+            const bool wideHasNext = (2 < nStages);
+            w.coMode = 2;
+            w.coTakeBelow = takeMain ? std::max(0, n - stages[0].grid) : 0;
+            w.resume = 0;
+            w.mainDone = ctx->dCounters.ptr + 14;
+            w.feedList = ctx->dOverflow.ptr;
+            w.feedCount = ctx->dCounters.ptr + 3;
+            w.feedCursor = ctx->dCounters.ptr + 2;
+            w.overflowList = wideHasNext ? ctx->dOverflow.ptr + static_cast<size_t>(n) : nullptr;
+            w.overflowCount = wideHasNext ? ctx->dCounters.ptr + 5 : nullptr;
+            w.tbScratch = ctx->dTb.ptr + tbNarrow;
+            w.tbStride = sw.tbStride;
+            w.stateCap = sw.cap;
+            unsigned long long *dTrace = nullptr;
+            if (ctx->dpTrace) {
+                TWL_CUDA(ctx, cudaMalloc(&dTrace, sizeof(unsigned long long) * 4 * (static_cast<size_t>(n) + 1)));
+                TWL_CUDA(ctx, cudaMemsetAsync(dTrace, 0, sizeof(unsigned long long) * 4 * (static_cast<size_t>(n) + 1), ctx->stream));
+                w.coTrace = dTrace; a.coTrace = dTrace;
+            }
+            TWL_CUDA(ctx, cudaEventRecord(ctx->evFork, ctx->stream));
+            TWL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->evFork, 0));
+            TWL_CUDA(ctx, twl::launchTalcoWavefront(sw.threads, sw.slots, matClass, w, sw.grid, ctx->stream2));
+            TWL_CUDA(ctx, cudaEventRecord(ctx->evJoin, ctx->stream2));
+            a.coMode = 1;
+            a.mainDone = w.mainDone; a.feedList = w.feedList; a.feedCount = w.feedCount; a.feedCursor = w.feedCursor;
+            a.overflowList = nullptr; a.overflowCount = nullptr;
+            TWL_CUDA(ctx, twl::launchTalcoWavefront(st.threads, st.slots, matClass, a, st.grid, ctx->stream));
+            TWL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
+            ctx->lastLaunches += 2;
+            if (dTrace) {
+                cudaStreamSynchronize(ctx->stream);
+                std::vector<unsigned long long> t(4 * (static_cast<size_t>(n) + 1));
+                cudaMemcpy(t.data(), dTrace, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+                cudaFree(dTrace);
+                a.coTrace = nullptr;
+                const unsigned long long endNarrow = t[4 * n], endWide = t[4 * n + 1];
+                unsigned long long t0 = ~0ull;
+                int mainByWide = 0;
+                for (int p = 0; p < n; ++p) { if (t[4 * p]) t0 = std::min(t0, t[4 * p]); if (t[4 * p + 3] == 1) ++mainByWide; }
+                std::fprintf(stderr, "[twl co-run] narrow grid %d, wide grid %d, main pairs done by wide workers %d; block 0 exits: narrow %+.3f ms, wide %+.3f ms after the first hand-over\n",
+                             st.grid, sw.grid, mainByWide, (double)(long long)(endNarrow - t0) * 1e-6, (double)(long long)(endWide - t0) * 1e-6);
+                for (int p = 0; p < n; ++p)
+                    if (t[4 * p])
+                        std::fprintf(stderr, "[twl co-run]   pair %5d handed over %+8.3f ms, taken after %7.3f ms, ran %7.3f ms\n", p, (double)(long long)(t[4 * p] - t0) * 1e-6,
+                                     (double)(long long)(t[4 * p + 1] - t[4 * p]) * 1e-6, (double)(long long)(t[4 * p + 2] - t[4 * p + 1]) * 1e-6);
+            }
+            ++s;   // stage 1 ran alongside
+            continue;
+        }
         if (st.kind == 3) TWL_CUDA(ctx, twl::launchTalcoWarp(matClass, a, st.grid, ctx->stream));
         else if (st.kind == 0) TWL_CUDA(ctx, twl::launchTalcoWavefront(st.threads, st.slots, matClass, a, st.grid, ctx->stream));
         else TWL_CUDA(ctx, twl::launchTalcoGeneric(ctx->P, st.kind == 2, a, st.grid, st.kind == 1 ? twl::genericStateWords(st.cap) * sizeof(float) : 0, ctx->stream));
@@ -417,6 +498,7 @@ int twl_set_option(twl_ctx *ctx, const char *name, int value) {
     if (std::strcmp(name, "force_generic") == 0) { ctx->forceGeneric = value != 0; return TWL_OK; }
     if (std::strcmp(name, "first_threads") == 0) { if (value != 96 && value != 128) return TWL_E_ARG; ctx->firstThreads = value; return TWL_OK; }
     if (std::strcmp(name, "wide_threads") == 0) { if (value != 256 && value != 512) return TWL_E_ARG; ctx->wideThreads = value; return TWL_OK; }
+    if (std::strcmp(name, "wide_workers") == 0) { ctx->wideWorkers = std::max(0, value); return TWL_OK; }
     if (std::strcmp(name, "dp_trace") == 0) { ctx->dpTrace = value; return TWL_OK; }
     if (std::strcmp(name, "latency_shape") == 0) { ctx->latencyShape = value; return TWL_OK; }   // 0: 256x2, 1: 512x1
     if (std::strcmp(name, "latency_mode") == 0) { ctx->latencyMode = value; return TWL_OK; }     // -1 auto, 0 off, 1 always

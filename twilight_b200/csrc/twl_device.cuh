@@ -74,6 +74,18 @@ struct TalcoArgs {
     size_t stateStride;      // in 4-byte words
     int stateCap;            // cells per wavefront array (excluding padding)
     int resume;              // this stage works on an overflow list: pairs continue at the tile recorded in `results`
+    // Co-running wide worker (talco_wavefront.cu): the narrow kernel and a few wide CTAs run at the same time. The narrow
+    // kernel hands pairs whose band outgrew its window to `feed*`; a wide CTA takes fed pairs first and otherwise works on
+    // the main queue like everybody else, so it never idles while there is work and overflowed pairs do not wait for the
+    // end of the stage.
+    int coMode;              // 0 off, 1 narrow producer (counts finished pairs in mainDone), 2 wide worker
+    int coTakeBelow;         // mode 2: also take main-queue entries with index below this (0 = never). Large batches only, and not
+                             // the last wave, so that pairs handed over near the end find an idle wide worker
+    int *mainDone;           // pairs of the main queue that are completely finished (either kernel)
+    int *feedList;           // mode 2: entries appended by the producers (-1 until written)
+    int *feedCount;          // mode 2: number of appended entries
+    int *feedCursor;         // mode 2: next entry to take
+    unsigned long long *coTrace;   // diagnostics (nullable): per pair [4] = handed over, taken, finished (globaltimer ns), taker's role
 };
 
 } // namespace twl
