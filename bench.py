@@ -123,7 +123,7 @@ def cpu_reference_level(ids, rows, weights, pairs, sample_pairs, threads):
     return cells / dt / 1e9, cells, dt, ("reference" if use_ref else "port")
 
 
-def run_msa(ctx, n_leaves, length, seed, repeats=2):
+def run_msa(ctx, n_leaves, length, seed, repeats=3):
     """Full progressive MSA of a synthetic RNASim-shaped set through the device-resident level pipeline
     (twl_rows_upload -> twl_align_level per guide-tree level -> twl_rows_download): sequences/s end to end and the
     per-phase device times with the HBM roofline of the two byte-moving kernels."""

@@ -60,6 +60,9 @@ struct TwlLevelState {
     DevBuf<char> dStage;
     PinBuf<char> hStage;
     bool lutReady = false;
+    cudaEvent_t stageFree = nullptr;      // recorded after the last asynchronous use of hStage / dStage / dCopies
+    bool stagePending = false;
+    std::vector<cudaEvent_t> sliceEv;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float phaseMs[4] = {0, 0, 0, 0};
 
@@ -76,6 +79,7 @@ TwlLevelState *levelOf(twl_ctx *ctx) {
     if (!ctx->level) {
         ctx->level = new TwlLevelState();
         for (auto &e : ctx->level->ev) cudaEventCreate(&e);
+        cudaEventCreateWithFlags(&ctx->level->stageFree, cudaEventDisableTiming);
     }
     return ctx->level;
 }
@@ -90,6 +94,17 @@ void parallelRows(int n, size_t bytes, const F &body) {
     for (int t = 1; t < nThreads; ++t) pool.emplace_back([&, t] { body(std::min(n, t * per), std::min(n, (t + 1) * per)); });
     body(0, std::min(n, per));
     for (auto &th : pool) th.join();
+}
+
+// cuts a transfer list into slices of about 8 MB (row boundaries): returns the first row of every slice plus n
+std::vector<int> sliceRows(const std::vector<twl::RowCopy> &list, int n) {
+    constexpr long long kSlice = 8 << 20;
+    std::vector<int> cuts{0};
+    long long start = 0;
+    for (int i = 0; i < n; ++i)
+        if (list[i].stageOff - start >= kSlice) { cuts.push_back(i); start = list[i].stageOff; }
+    cuts.push_back(n);
+    return cuts;
 }
 
 cudaError_t poolAlloc(TwlLevelState *L, size_t bytes, char **out) {
@@ -194,6 +209,8 @@ void twlLevelDestroy(twl_ctx *ctx) {
     L->hRes.release(); L->hUps.release(); L->hNeedHost.release(); L->hFinal.release(); L->hSides.release(); L->hFreqPin.release(); L->hMergedPin.release();
     L->dUps2.release(); L->dUpdPair.release(); L->dNeedHost.release(); L->dUpdIn.release();
     for (auto &e : L->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : L->sliceEv) cudaEventDestroy(e);
+    if (L->stageFree) cudaEventDestroy(L->stageFree);
     delete L;
     ctx->level = nullptr;
 }
@@ -236,15 +253,24 @@ int twl_rows_upload(twl_ctx *ctx, int n, const int32_t *ids, const char *const *
         list[i].dev = r.buf[0]; list[i].stageOff = static_cast<long long>(total); list[i].len = lens[i]; list[i].pad = 0;
         total += (static_cast<size_t>(lens[i]) + 15) & ~static_cast<size_t>(15);
     }
+    if (L->stagePending) { TWL_CUDA(ctx, cudaEventSynchronize(L->stageFree)); L->stagePending = false; }   // an earlier upload may still read the staging buffers
     TWL_CUDA(ctx, L->hStage.reserve(std::max<size_t>(total, 16)));
     TWL_CUDA(ctx, L->dStage.reserve(std::max<size_t>(total, 16)));
     TWL_CUDA(ctx, L->dCopies.reserve(n));
-    parallelRows(n, total, [&](int b, int e) { for (int i = b; i < e; ++i) std::memcpy(L->hStage.ptr + list[i].stageOff, rows[i], lens[i]); });
-    TWL_CUDA(ctx, cudaMemcpyAsync(L->dStage.ptr, L->hStage.ptr, total, cudaMemcpyHostToDevice, ctx->stream));
+    // staged in slices: the H2D copy of one slice runs while the host fills the next; the call returns with the copies and
+    // the scatter kernel enqueued (stream order makes later calls see the rows), the staging buffer is fenced by an event
+    const std::vector<int> cuts = sliceRows(list, n);
+    for (size_t c = 0; c + 1 < cuts.size(); ++c) {
+        const int b0 = cuts[c], e0 = cuts[c + 1];
+        const size_t from = static_cast<size_t>(list[b0].stageOff), to = (e0 < n) ? static_cast<size_t>(list[e0].stageOff) : total;
+        parallelRows(e0 - b0, to - from, [&](int b, int e) { for (int i = b0 + b; i < b0 + e; ++i) std::memcpy(L->hStage.ptr + list[i].stageOff, rows[i], lens[i]); });
+        TWL_CUDA(ctx, cudaMemcpyAsync(L->dStage.ptr + from, L->hStage.ptr + from, to - from, cudaMemcpyHostToDevice, ctx->stream));
+    }
     TWL_CUDA(ctx, cudaMemcpyAsync(L->dCopies.ptr, list.data(), sizeof(twl::RowCopy) * n, cudaMemcpyHostToDevice, ctx->stream));
     twl::rowTransferKernel<<<(n * 32 + 255) / 256, 256, 0, ctx->stream>>>(L->dCopies.ptr, n, L->dStage.ptr, 1);
     TWL_CUDA(ctx, cudaGetLastError());
-    TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    TWL_CUDA(ctx, cudaEventRecord(L->stageFree, ctx->stream));
+    L->stagePending = true;
     return TWL_OK;
 }
 
@@ -268,20 +294,34 @@ int twl_rows_download(twl_ctx *ctx, int n, const int32_t *ids, char *const *dst,
         list[i].dev = r.buf[r.storage]; list[i].stageOff = static_cast<long long>(total); list[i].len = r.len; list[i].pad = 0;
         total += (static_cast<size_t>(r.len) + 15) & ~static_cast<size_t>(15);
     }
+    if (L->stagePending) { TWL_CUDA(ctx, cudaEventSynchronize(L->stageFree)); L->stagePending = false; }   // an earlier upload may still read the staging buffers
     TWL_CUDA(ctx, L->hStage.reserve(std::max<size_t>(total, 16)));
     TWL_CUDA(ctx, L->dStage.reserve(std::max<size_t>(total, 16)));
     TWL_CUDA(ctx, L->dCopies.reserve(n));
     TWL_CUDA(ctx, cudaMemcpyAsync(L->dCopies.ptr, list.data(), sizeof(twl::RowCopy) * n, cudaMemcpyHostToDevice, ctx->stream));
     twl::rowTransferKernel<<<(n * 32 + 255) / 256, 256, 0, ctx->stream>>>(L->dCopies.ptr, n, L->dStage.ptr, 0);
     TWL_CUDA(ctx, cudaGetLastError());
-    TWL_CUDA(ctx, cudaMemcpyAsync(L->hStage.ptr, L->dStage.ptr, total, cudaMemcpyDeviceToHost, ctx->stream));
-    TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    parallelRows(n, total, [&](int b, int e) {
-        for (int i = b; i < e; ++i) {
-            std::memcpy(dst[i], L->hStage.ptr + list[i].stageOff, list[i].len);
-            if (lens) lens[i] = list[i].len;
-        }
-    });
+    // slices: the host unpacks one slice while the D2H copy of the next is in flight
+    const std::vector<int> cuts = sliceRows(list, n);
+    const size_t nSlices = cuts.size() - 1;
+    while (L->sliceEv.size() < nSlices) { cudaEvent_t e; TWL_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); L->sliceEv.push_back(e); }
+    for (size_t c = 0; c < nSlices; ++c) {
+        const int b0 = cuts[c], e0 = cuts[c + 1];
+        const size_t from = static_cast<size_t>(list[b0].stageOff), to = (e0 < n) ? static_cast<size_t>(list[e0].stageOff) : total;
+        TWL_CUDA(ctx, cudaMemcpyAsync(L->hStage.ptr + from, L->dStage.ptr + from, to - from, cudaMemcpyDeviceToHost, ctx->stream));
+        TWL_CUDA(ctx, cudaEventRecord(L->sliceEv[c], ctx->stream));
+    }
+    for (size_t c = 0; c < nSlices; ++c) {
+        const int b0 = cuts[c], e0 = cuts[c + 1];
+        const size_t from = static_cast<size_t>(list[b0].stageOff), to = (e0 < n) ? static_cast<size_t>(list[e0].stageOff) : total;
+        TWL_CUDA(ctx, cudaEventSynchronize(L->sliceEv[c]));
+        parallelRows(e0 - b0, to - from, [&](int b, int e) {
+            for (int i = b0 + b; i < b0 + e; ++i) {
+                std::memcpy(dst[i], L->hStage.ptr + list[i].stageOff, list[i].len);
+                if (lens) lens[i] = list[i].len;
+            }
+        });
+    }
     return TWL_OK;
 }
 
@@ -667,12 +707,19 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
         }
         if (out.status != 0) continue;
         out.path_len = u.pathLen;
-        if (paths && paths[begin + p]) std::memcpy(paths[begin + p], L->hFinal.ptr + u.pathOff, static_cast<size_t>(u.pathLen));
         if (u.mergedOff >= 0) {
             out.cached |= 4;
             kp.merged.assign(hMerged + u.mergedOff, hMerged + u.mergedOff + static_cast<size_t>(u.pathLen) * P);
         }
     }
+    if (paths && nu)
+        parallelRows(n, finalBytes, [&](int b, int e) {
+            for (int p = b; p < e; ++p) {
+                const twl_level_result &out = results[begin + p];
+                if (upOfPair[p] < 0 || out.status != 0 || !paths[begin + p]) continue;
+                std::memcpy(paths[begin + p], L->hFinal.ptr + L->hUps.ptr[upOfPair[p]].pathOff, static_cast<size_t>(out.path_len));
+            }
+        });
     tr.mark("results to caller (host)");
     const bool updateTimed = nu > 0;
     for (int i = 0; i < 3; ++i) {
