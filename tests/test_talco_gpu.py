@@ -288,3 +288,32 @@ def test_co_running_wide_workers_match_port(workers):
             assert o.cells == cells and o.tiles == tiles
             assert np.array_equal(o.path, path)
     ctx.close()
+
+
+def test_co_run_survives_serialised_kernels():
+    """CUDA_LAUNCH_BLOCKING=1 (or a profiler's kernel replay) runs the wide workers to completion before the narrow kernel
+    starts: they must give up waiting, and the clean-up launch must finish the pairs handed over afterwards."""
+    import subprocess, sys, os, textwrap
+    code = textwrap.dedent('''
+        import numpy as np, twilight_b200
+        from tests import oracle_lib as ol
+        from tests.helpers import synthetic_records
+        cfg, _, _, _, recs = synthetic_records(2, 2400, 19, 1024)
+        r = recs[0]
+        pairs, keys = [], []
+        for k in range(200):
+            xdrop = 9000 if k % 7 == 0 else 5000
+            pairs.append(twilight_b200.ProfilePairIn(r.profile[0], r.profile[1], r.gap_op[0], r.gap_ex[0], r.gap_op[1], r.gap_ex[1], 1, 1, xdrop=xdrop))
+            keys.append(xdrop)
+        want = {x: ol.port_talco(ol.TalcoCfg(xdrop=x), r.profile[0], r.profile[1], r.gap_op[0], r.gap_ex[0], r.gap_op[1], r.gap_ex[1], 1, 1) for x in set(keys)}
+        ctx = twilight_b200.Context(marker=1024)
+        outs = ctx.align_profiles(pairs)
+        for o, x in zip(outs, keys):
+            path, err, cells, tiles, _ = want[x]
+            assert o.status == err == 0 and o.cells == cells and np.array_equal(o.path, path)
+        print("serialised-ok")
+    ''')
+    env = dict(os.environ, CUDA_LAUNCH_BLOCKING="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert "serialised-ok" in out.stdout, out.stdout + out.stderr

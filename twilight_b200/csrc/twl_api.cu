@@ -324,7 +324,8 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
         if (st.kind == 2) stateWords = twl::genericStateWords(st.cap) * static_cast<size_t>(st.grid);
     }
     const size_t tbNarrow = coRun ? stages[0].tbStride * static_cast<size_t>(stages[0].grid) : 0;
-    if (coRun) tbBytes = std::max(tbBytes, tbNarrow + stages[1].tbStride * static_cast<size_t>(stages[1].grid));
+    if (coRun) tbBytes = std::max({tbBytes, tbNarrow + stages[1].tbStride * static_cast<size_t>(stages[1].grid),
+                                   stages[1].tbStride * static_cast<size_t>(std::min(n, ctx->smCount))});
     TWL_CUDA(ctx, ctx->dTb.reserve(tbBytes));
     if (stateWords) TWL_CUDA(ctx, ctx->dState.reserve(stateWords));
     const int nStages = static_cast<int>(stages.size());
@@ -372,6 +373,7 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
             w.coTakeBelow = takeMain ? std::max(0, n - stages[0].grid) : 0;
             w.resume = 0;
             w.mainDone = ctx->dCounters.ptr + 14;
+            w.heartbeat = ctx->dCounters.ptr + 15;
             w.feedList = ctx->dOverflow.ptr;
             w.feedCount = ctx->dCounters.ptr + 3;
             w.feedCursor = ctx->dCounters.ptr + 2;
@@ -391,7 +393,7 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
             TWL_CUDA(ctx, twl::launchTalcoWavefront(sw.threads, sw.slots, matClass, w, sw.grid, ctx->stream2));
             TWL_CUDA(ctx, cudaEventRecord(ctx->evJoin, ctx->stream2));
             a.coMode = 1;
-            a.mainDone = w.mainDone; a.feedList = w.feedList; a.feedCount = w.feedCount; a.feedCursor = w.feedCursor;
+            a.mainDone = w.mainDone; a.heartbeat = w.heartbeat; a.feedList = w.feedList; a.feedCount = w.feedCount; a.feedCursor = w.feedCursor;
             a.overflowList = nullptr; a.overflowCount = nullptr;
             TWL_CUDA(ctx, twl::launchTalcoWavefront(st.threads, st.slots, matClass, a, st.grid, ctx->stream));
             TWL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
@@ -412,6 +414,17 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
                     if (t[4 * p])
                         std::fprintf(stderr, "[twl co-run]   pair %5d handed over %+8.3f ms, taken after %7.3f ms, ran %7.3f ms\n", p, (double)(long long)(t[4 * p] - t0) * 1e-6,
                                      (double)(long long)(t[4 * p + 1] - t[4 * p]) * 1e-6, (double)(long long)(t[4 * p + 2] - t[4 * p + 1]) * 1e-6);
+            }
+            // clean-up: pairs handed over after the wide workers had left (only when the two kernels did not overlap); the
+            // launch continues the feed cursor and exits at once when nothing is pending
+            {
+                twl::TalcoArgs c = w;
+                c.coMode = 0; c.coTakeBelow = 0; c.coTrace = nullptr;
+                c.order = w.feedList; c.queue = w.feedCursor; c.nWorkPtr = w.feedCount;
+                c.resume = 1;
+                c.tbScratch = ctx->dTb.ptr;
+                TWL_CUDA(ctx, twl::launchTalcoWavefront(sw.threads, sw.slots, matClass, c, std::min(n, ctx->smCount), ctx->stream));
+                ctx->lastLaunches += 1;
             }
             ++s;   // stage 1 ran alongside
             continue;

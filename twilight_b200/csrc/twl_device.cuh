@@ -82,6 +82,8 @@ struct TalcoArgs {
     int coTakeBelow;         // mode 2: also take main-queue entries with index below this (0 = never). Large batches only, and not
                              // the last wave, so that pairs handed over near the end find an idle wide worker
     int *mainDone;           // pairs of the main queue that are completely finished (either kernel)
+    int *heartbeat;          // bumped by the narrow kernel at every tile: lets a waiting wide worker tell "still running" from
+                             // "not running at all" (kernels serialised by a profiler or CUDA_LAUNCH_BLOCKING)
     int *feedList;           // mode 2: entries appended by the producers (-1 until written)
     int *feedCount;          // mode 2: number of appended entries
     int *feedCursor;         // mode 2: next entry to take
