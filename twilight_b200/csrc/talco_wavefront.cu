@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(NT, (NT == 96 ? 6 : (NT <= 128 ? 640 / NT : (N
     uint8_t *tb = a.tbScratch + static_cast<size_t>(blockIdx.x) * a.tbStride;   // tb[k][rho], row stride W
     const int marker = a.marker;
     const int rho0 = tid * kSlots;
+    if (a.coMode == 1 && tid == 0) atomicAdd(a.heartbeat, 1);
 
     for (;;) {
         __syncthreads();
@@ -123,7 +124,8 @@ __global__ void __launch_bounds__(NT, (NT == 96 ? 6 : (NT <= 128 ? 640 / NT : (N
                         }
                         continue;
                     }
-                    if (*reinterpret_cast<volatile int *>(a.queue) < a.coTakeBelow) {
+                    // main-queue work only while the narrow kernel is demonstrably running (its CTAs beat once when they start)
+                    if (*reinterpret_cast<volatile int *>(a.heartbeat) != 0 && *reinterpret_cast<volatile int *>(a.queue) < a.coTakeBelow) {
                         const int w = atomicAdd(a.queue, 1);
                         if (w < nMain) { got = a.order[w]; break; }
                     }
