@@ -157,7 +157,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_sample = max(threads, min(args.pairs, 4 * threads))
+    n_sample = max(threads, min(args.pairs, 16 * threads))
     ids, rows, weights, pairs = build_level_batch(n_sample, args.length, seed=1000)
     vals, ms = [], []
     kind = "port"
@@ -338,7 +338,7 @@ def main():
             line["msa"] = run_msa(ctx, args.msa_leaves, args.length, seed=77)
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            n_sample = max(threads, min(len(pairs), 4 * threads))
+            n_sample = max(threads, min(len(pairs), 16 * threads))
             g, c, dt, kind = cpu_reference_level(ids, rows, weights, pairs, n_sample, threads)
             line["cpu_baseline"] = {"value": g, "unit": "GCUPS", "cores": threads, "kind": kind,
                                     "sample": f"the first {n_sample} pairs of the step's level ({c} cells, {dt:.1f} s): the reference's whole per-pair "

@@ -84,10 +84,22 @@ TwlLevelState *levelOf(twl_ctx *ctx) {
     return ctx->level;
 }
 
+// Host threads for staging copies: up to 8, but the host's cores are shared by one process per GPU (TWL_HOST_THREADS overrides).
+int hostCopyThreads() {
+    static const int n = [] {
+        if (const char *e = std::getenv("TWL_HOST_THREADS")) return std::max(1, std::atoi(e));
+        int gpus = 1;
+        if (cudaGetDeviceCount(&gpus) != cudaSuccess || gpus < 1) gpus = 1;
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        return static_cast<int>(std::min<unsigned>(8u, std::max(1u, hw / static_cast<unsigned>(gpus))));
+    }();
+    return n;
+}
+
 // splits [0, n) over a few host threads (staging copies of many small rows are memory-latency bound on one core)
 template <typename F>
 void parallelRows(int n, size_t bytes, const F &body) {
-    const int nThreads = (bytes > (static_cast<size_t>(4) << 20)) ? static_cast<int>(std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()))) : 1;
+    const int nThreads = (bytes > (static_cast<size_t>(4) << 20)) ? hostCopyThreads() : 1;
     if (nThreads == 1) { body(0, n); return; }
     std::vector<std::thread> pool;
     const int per = (n + nThreads - 1) / nThreads;
