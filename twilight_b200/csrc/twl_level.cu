@@ -84,12 +84,13 @@ TwlLevelState *levelOf(twl_ctx *ctx) {
     return ctx->level;
 }
 
-// Host threads for staging copies: up to 8, but the host's cores are shared by one process per GPU (TWL_HOST_THREADS overrides).
+// Host threads for staging copies: up to 8, but the host's cores are shared by the ranks of a multi-GPU job (TWL_HOST_THREADS overrides).
 int hostCopyThreads() {
     static const int n = [] {
         if (const char *e = std::getenv("TWL_HOST_THREADS")) return std::max(1, std::atoi(e));
-        int gpus = 1;
-        if (cudaGetDeviceCount(&gpus) != cudaSuccess || gpus < 1) gpus = 1;
+        int gpus = 1;   // processes sharing this host: torchrun / mpirun export it
+        for (const char *name : {"LOCAL_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_SIZE", "MPI_LOCALNRANKS"})
+            if (const char *e = std::getenv(name)) { gpus = std::max(1, std::atoi(e)); break; }
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
         return static_cast<int>(std::min<unsigned>(8u, std::max(1u, hw / static_cast<unsigned>(gpus))));
     }();
