@@ -173,7 +173,11 @@ int twl_last_launch_count(const twl_ctx *ctx);
 /* Tuning / diagnostics switches. "force_generic" = 1 routes nucleotide batches through the wide-band generic kernel
  * instead of the register-resident wavefront kernel (results are identical; used by the A/B parity tests).
  * "dp_kernel" = 1 (default) one pair per CTA, register-resident wavefront; 2 = experimental one pair per warp
- * (talco_warp.cu; same results, currently slower); 0 = choose by batch size. "warp_ctas_per_sm", "warp_min_pairs" tune 2/0. */
+ * (talco_warp.cu; same results, currently slower); 0 = choose by batch size. "warp_ctas_per_sm", "warp_min_pairs" tune 2/0.
+ * "wide_workers" (default 8; 0 = run the wide-band kernel after the narrow one instead of beside it), "wide_threads"
+ * (512 or 256), "first_threads" (128 or 96), "latency_mode" (-1 auto, 0 off, 1 always) and "latency_shape" (0..3) select
+ * among bit-identical schedules / instantiations of the wavefront kernel; "dp_trace" = 1 prints per-stage times to stderr.
+ * The environment variable TWL_OPTIONS="name=value,name=value" applies the same switches at twl_init. */
 int twl_set_option(twl_ctx *ctx, const char *name, int value);
 
 /* Device self-test: evaluates the reciprocal-based exact division used by the DP kernels and the IEEE divide on n

@@ -1,9 +1,10 @@
 // talco_wavefront.cu — the fast TALCO-XDrop kernel for nucleotide profiles (P = 6): one pair per CTA, the anti-diagonal
 // wavefront lives in REGISTERS.
 //
-// Mapping. A CTA of NT threads owns W = 4*NT consecutive query rows at a time. Row i is handled by "slot"
-// rho = i mod W, i.e. thread rho/4, register slot rho%4 (a thread owns 4 consecutive rows); as the live band [L,U] of
-// the X-drop recurrence slides along the query, a thread whose rows fell below L is re-assigned to rows + W. Per
+// Mapping. A CTA of NT threads owns W = KS*NT consecutive query rows at a time (KS rows per thread; 128 x 4 is the
+// throughput instantiation, 512 x 2 the wide / low-latency one). Row i is handled by "slot" rho = i mod W, i.e. thread
+// rho/KS, register slot rho%KS (a thread owns KS consecutive rows); as the live band [L,U] of the X-drop recurrence
+// slides along the query, a thread whose rows fell below L is re-assigned to rows + W (W need not be a power of two). Per
 // slot the thread keeps, in registers, the query column (6 counts + 2 position-specific gap penalties) and the
 // H / I / D scores of the previous two anti-diagonals, so per cell and per diagonal the only memory traffic is one
 // 32-byte reference column (two LDG.128 that hit L1; the lines needed a few diagonals ahead are prefetched) and one
@@ -20,8 +21,9 @@
 // that the stale slots the reference reads are reproduced — the tile stop rule, the traceback start cell and the
 // per-tile path concatenation of Align_freq (:62-108).
 //
-// A band wider than W-3 cannot be held; the pair is then appended to an overflow list and re-run by a wider
-// instantiation or by the generic kernel (talco_generic.cu).
+// A band wider than W-(KS-1) cannot be held; the pair keeps its finished tiles and is handed to a wider instantiation
+// (running at the same time, see TalcoArgs::coMode, or launched afterwards) or to the generic kernel (talco_generic.cu),
+// which resume it at the failing tile.
 #include "talco_score.cuh"
 #include "twl_device.cuh"
 
