@@ -262,8 +262,8 @@ def test_narrow_window_variant_overflows_to_wide():
     ctx.close()
 
 
-@pytest.mark.parametrize("workers", [0, 1, 8])
-def test_co_running_wide_workers_match_port(workers):
+@pytest.mark.parametrize("workers,every", [(0, 5), (1, 5), (8, 5), (8, 1)])
+def test_co_running_wide_workers_match_port(workers, every):
     """More pairs than SMs: the narrow kernel and the wide workers run at the same time (twl_set_option wide_workers);
     pairs whose band outgrows 512 rows are handed over mid-flight. Same bits as the oracle, with and without co-run."""
     import twilight_b200
@@ -271,7 +271,7 @@ def test_co_running_wide_workers_match_port(workers):
     r = recs[0]
     pairs, want = [], []
     for k in range(320):
-        xdrop = (5000, 9000, 14000, 40000)[k % 4] if k % 5 == 0 else 5000
+        xdrop = (9000, 14000, 40000, 9000)[k % 4] if k % every == 0 else 5000     # every == 1: every pair outgrows the narrow window
         key = xdrop
         pairs.append(twilight_b200.ProfilePairIn(r.profile[0], r.profile[1], r.gap_op[0], r.gap_ex[0], r.gap_op[1], r.gap_ex[1], 1, 1, xdrop=xdrop))
         want.append(key)

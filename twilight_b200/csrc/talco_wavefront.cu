@@ -108,12 +108,15 @@ __global__ void __launch_bounds__(NT, (NT == 96 ? 6 : (NT <= 128 ? 640 / NT : (N
         __syncthreads();
         if (tid == 0) {
             if (a.coMode == 2) {
-                // wide worker: fed pairs first, then the main queue; leave when every main pair is finished and nothing is fed
+                // wide worker: fed pairs first, then the main queue; leave when every main pair is finished
                 const int nMain = *a.nWorkPtr;
                 int got = -1, fed = 0;
                 int lastBeat = *reinterpret_cast<volatile int *>(a.heartbeat);
                 unsigned long long lastChange = globalTimerNs();
                 for (;;) {
+                    // Every main pair finished: nothing more will be handed over. What is still queued is better served by
+                    // the clean-up launch that follows (one CTA per SM) than by the few wide workers one after the other.
+                    if (*reinterpret_cast<volatile int *>(a.mainDone) >= nMain) break;
                     const int cur = *reinterpret_cast<volatile int *>(a.feedCursor);
                     if (cur < *reinterpret_cast<volatile int *>(a.feedCount)) {
                         if (atomicCAS(a.feedCursor, cur, cur + 1) == cur) {
@@ -131,8 +134,6 @@ __global__ void __launch_bounds__(NT, (NT == 96 ? 6 : (NT <= 128 ? 640 / NT : (N
                         const int w = atomicAdd(a.queue, 1);
                         if (w < nMain) { got = a.order[w]; break; }
                     }
-                    if (*reinterpret_cast<volatile int *>(a.mainDone) >= nMain &&
-                        *reinterpret_cast<volatile int *>(a.feedCursor) >= *reinterpret_cast<volatile int *>(a.feedCount)) break;
                     // Watchdog: the producers bump the heartbeat every tile (a few ms at most). No beat for 50 ms means the narrow
                     // kernel is not running next to us (profiler replay, CUDA_LAUNCH_BLOCKING): leave; whatever is handed over later
                     // is picked up by the clean-up launch that follows both kernels.
