@@ -189,7 +189,7 @@ def test_warp_per_pair_kernel_matches_port():
         assert np.array_equal(o.path, r.aln_wo), f"pair {k}"
 
 
-@pytest.mark.parametrize("shape", [0, 1, 2, 3])
+@pytest.mark.parametrize("shape", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("n,L,seed,marker", [(12, 900, 29, 128), (6, 2500, 31, 1024)])
 def test_low_latency_variant_matches_port(n, L, seed, marker, shape):
     """The instantiations used for levels with few pairs (twl_set_option latency_mode=1): 256 threads x 2 rows (shape 0)
@@ -207,7 +207,7 @@ def test_low_latency_variant_matches_port(n, L, seed, marker, shape):
         assert np.array_equal(o.path, r.aln_wo), f"pair {k}"
 
 
-@pytest.mark.parametrize("shape", [0, 1, 2, 3])
+@pytest.mark.parametrize("shape", [0, 1, 2, 3, 4])
 def test_low_latency_variant_overflows_to_wide(shape):
     """Bands wider than the 512-row window of the low-latency variant continue in the 1024-row kernel (and beyond),
     same bits as the oracle."""

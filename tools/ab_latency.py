@@ -5,7 +5,7 @@ import numpy as np
 import bench, twilight_b200
 
 leaves = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
-for mode, shape in ((0, 0), (-1, 1), (-1, 2), (-1, 3), (1, 2)):
+for mode, shape in ((-1, 2), (-1, 4), (1, 4)):
     ctx = twilight_b200.Context()
     ctx.set_option("latency_mode", mode)
     ctx.set_option("latency_shape", shape)

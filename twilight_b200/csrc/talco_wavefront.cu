@@ -31,8 +31,8 @@ namespace twl {
 
 
 struct WaveShared {
-    int4 red[2][16];            // per warp: (max score as ordered int, first live row, last live row, -)
-    float2 edge[2][16];         // per warp: H and I of the warp's last slot (row-neighbour of the next warp's first slot)
+    int4 red[2][32];            // per warp: (max score as ordered int, first live row, last live row, -)
+    float2 edge[2][32];         // per warp: H and I of the warp's last slot (row-neighbour of the next warp's first slot)
     unsigned convMask[3];
     int8_t ops[2 * kMaxMarker + 16];
     int refOff, qryOff, lastTile, error, nOps, opsBegin, tailLen, tailOp;
@@ -497,8 +497,8 @@ __global__ void __launch_bounds__(NT, (NT == 96 ? 6 : (NT <= 128 ? 640 / NT : (N
                 const int wMax = __reduce_max_sync(0xffffffffu, orderedInt(myMax));
                 const int wLo = __reduce_min_sync(0xffffffffu, myLo);
                 const int wHi = __reduce_max_sync(0xffffffffu, myHi);
-                if (lane == 31) edgeOut[g0 * 16] = make_float2(h1[kSlots - 1], i1[kSlots - 1]);
-                if (lane == 0) redOut[g0 * 16] = make_int4(wMax, wLo, wHi, 0);
+                if (lane == 31) edgeOut[g0 * 32] = make_float2(h1[kSlots - 1], i1[kSlots - 1]);
+                if (lane == 0) redOut[g0 * 32] = make_int4(wMax, wLo, wHi, 0);
                 __syncthreads();
                 int oMax, newL, newU;
                 if (NW > 8) {           // many warps: one shared-memory read per lane and three warp reductions
@@ -696,6 +696,7 @@ static cudaError_t launchMc(int threads, int slots, const TalcoArgs &args, int g
     else if (threads == 256 && slots == 2) talcoWavefrontKernel<256, MC, 2><<<grid, 256, 0, stream>>>(args);
     else if (threads == 512 && slots == 1) talcoWavefrontKernel<512, MC, 1><<<grid, 512, 0, stream>>>(args);
     else if (threads == 512 && slots == 2) talcoWavefrontKernel<512, MC, 2><<<grid, 512, 0, stream>>>(args);
+    else if (threads == 1024 && slots == 1) talcoWavefrontKernel<1024, MC, 1><<<grid, 1024, 0, stream>>>(args);
     else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
@@ -708,9 +709,9 @@ int wavefrontMaxCtasPerSm(int threads, int slots, int matClass) {
     int n = 0;
 #define TWL_OCC(NT_, MC_, KS_) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, talcoWavefrontKernel<NT_, MC_, KS_>, NT_, 0)
     if (matClass == 1) {
-        if (threads == 128 && slots == 4) TWL_OCC(128, 1, 4); else if (threads == 96 && slots == 4) TWL_OCC(96, 1, 4); else if (threads == 256 && slots == 4) TWL_OCC(256, 1, 4); else if (threads == 256 && slots == 2) TWL_OCC(256, 1, 2); else if (threads == 512 && slots == 1) TWL_OCC(512, 1, 1); else if (threads == 512 && slots == 2) TWL_OCC(512, 1, 2);
+        if (threads == 128 && slots == 4) TWL_OCC(128, 1, 4); else if (threads == 96 && slots == 4) TWL_OCC(96, 1, 4); else if (threads == 256 && slots == 4) TWL_OCC(256, 1, 4); else if (threads == 256 && slots == 2) TWL_OCC(256, 1, 2); else if (threads == 512 && slots == 1) TWL_OCC(512, 1, 1); else if (threads == 512 && slots == 2) TWL_OCC(512, 1, 2); else if (threads == 1024 && slots == 1) TWL_OCC(1024, 1, 1);
     } else {
-        if (threads == 128 && slots == 4) TWL_OCC(128, 0, 4); else if (threads == 96 && slots == 4) TWL_OCC(96, 0, 4); else if (threads == 256 && slots == 4) TWL_OCC(256, 0, 4); else if (threads == 256 && slots == 2) TWL_OCC(256, 0, 2); else if (threads == 512 && slots == 1) TWL_OCC(512, 0, 1); else if (threads == 512 && slots == 2) TWL_OCC(512, 0, 2);
+        if (threads == 128 && slots == 4) TWL_OCC(128, 0, 4); else if (threads == 96 && slots == 4) TWL_OCC(96, 0, 4); else if (threads == 256 && slots == 4) TWL_OCC(256, 0, 4); else if (threads == 256 && slots == 2) TWL_OCC(256, 0, 2); else if (threads == 512 && slots == 1) TWL_OCC(512, 0, 1); else if (threads == 512 && slots == 2) TWL_OCC(512, 0, 2); else if (threads == 1024 && slots == 1) TWL_OCC(1024, 0, 1);
     }
 #undef TWL_OCC
     return n;

@@ -279,9 +279,10 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
         // few pairs (every CTA has an SM to itself): 256 threads x 2 rows shortens the per-thread instruction stream of a
         // diagonal, which is what bounds a lone CTA; otherwise 128 threads x 4 rows, 5 CTAs per SM
         const bool lowLatency = !useWarp && ctx->latencyMode != 0 && (ctx->latencyMode == 1 || n <= ctx->smCount);
-        // latency shapes: 0 = 256x2 then 256x4, 1 = 512x1 then 256x4, 2 = 512x2 (1024-row window at once), 3 = 512x1 then 512x2
-        static const int shapes[4][2][2] = {{{256, 2}, {256, 4}}, {{512, 1}, {256, 4}}, {{512, 2}, {0, 0}}, {{512, 1}, {512, 2}}};
-        const int sh = std::min(std::max(ctx->latencyShape, 0), 3);
+        // latency shapes: 0 = 256x2 then 256x4, 1 = 512x1 then 256x4, 2 = 512x2 (1024-row window at once), 3 = 512x1 then 512x2,
+        // 4 = 1024x1 (1024-row window, one row per thread)
+        static const int shapes[5][2][2] = {{{256, 2}, {256, 4}}, {{512, 1}, {256, 4}}, {{512, 2}, {0, 0}}, {{512, 1}, {512, 2}}, {{1024, 1}, {0, 0}}};
+        const int sh = std::min(std::max(ctx->latencyShape, 0), 4);
         int plan[4][2] = {{ctx->firstThreads, 4}, {ctx->wideThreads, ctx->wideThreads == 512 ? 2 : 4}, {0, 0}, {0, 0}};
         if (lowLatency) { plan[0][0] = shapes[sh][0][0]; plan[0][1] = shapes[sh][0][1]; plan[1][0] = shapes[sh][1][0]; plan[1][1] = shapes[sh][1][1]; }
         for (int s = 0; plan[s][0]; ++s) {
