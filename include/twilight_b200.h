@@ -99,7 +99,9 @@ int twl_batch_fetch(twl_ctx *ctx, int8_t *const *paths, twl_pair_result *results
  *      (SequenceInfo::id). ------------------------------------------------------------------------------------- */
 int twl_rows_upload(twl_ctx *ctx, int n, const int32_t *ids, const char *const *rows, const int32_t *lens, const float *weights);
 int twl_rows_download(twl_ctx *ctx, int n, const int32_t *ids, char *const *dst, int32_t *lens);   /* dst[i] holds >= current length */
-int twl_rows_length(twl_ctx *ctx, int32_t id);   /* current length of a row, <0 if unknown */
+int twl_rows_length(twl_ctx *ctx, int32_t id);
+/* The same for n rows at once: lens[i] = current length of row ids[i], or -1. */
+int twl_rows_lengths(twl_ctx *ctx, int n, const int32_t *ids, int32_t *lens);   /* current length of a row, <0 if unknown */
 int twl_rows_clear(twl_ctx *ctx);
 
 /* ---- one guide-tree level on the resident rows: for every pair calculateProfile + getConsensus +

@@ -56,6 +56,7 @@ SIGNATURES = {
     "twl_rows_upload": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_char_p), C.POINTER(C.c_int32), C.POINTER(C.c_float)]),
     "twl_rows_download": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
     "twl_rows_length": (C.c_int, [C.c_void_p, C.c_int32]),
+    "twl_rows_lengths": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "twl_rows_clear": (C.c_int, [C.c_void_p]),
     "twl_align_level": (C.c_int, [C.c_void_p, C.POINTER(LevelPair), C.c_int, C.c_int, C.c_float, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(LevelResult)]),
     "twl_level_fetch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),

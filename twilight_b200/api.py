@@ -196,13 +196,23 @@ class Context:
 
     def rows_download(self, ids: Sequence[int]) -> List[bytes]:
         n = len(ids)
-        a_ids = (C.c_int32 * n)(*[int(i) for i in ids])
-        lens = [self._lib.twl_rows_length(self._h, int(i)) for i in ids]
-        bufs = [C.create_string_buffer(max(l, 1)) for l in lens]
-        ptrs = (C.c_void_p * n)(*[C.addressof(b) for b in bufs])
-        out_l = (C.c_int32 * n)()
-        self._check(self._lib.twl_rows_download(self._h, n, a_ids, ptrs, out_l))
-        return [bufs[k].raw[:out_l[k]] for k in range(n)]
+        a_ids = np.asarray(ids, np.int32)
+        lens32 = np.zeros(max(n, 1), np.int32)
+        self._check(self._lib.twl_rows_lengths(self._h, n, a_ids.ctypes.data_as(C.POINTER(C.c_int32)), lens32.ctypes.data_as(C.POINTER(C.c_int32))))
+        lens = lens32[:n].astype(np.int64)
+        if n and lens.min() < 0:
+            raise TwilightError(f"twl_rows_download: unknown row id {int(a_ids[int(np.argmin(lens))])}")
+        offs = np.concatenate([[0], np.cumsum((lens + 15) & ~15)]).astype(np.int64)
+        need = int(offs[-1]) + 16
+        if getattr(self, "_dl_buf", None) is None or self._dl_buf.size < need:     # one reused buffer, one pointer table
+            self._dl_buf = np.empty(need + need // 4, np.uint8)
+        buf = self._dl_buf
+        ptrs = (buf.ctypes.data + offs[:-1]).astype(np.uint64)
+        out_l = np.zeros(max(n, 1), np.int32)
+        self._check(self._lib.twl_rows_download(self._h, n, a_ids.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                ptrs.ctypes.data_as(C.POINTER(C.c_void_p)), out_l.ctypes.data_as(C.POINTER(C.c_int32))))
+        mv = memoryview(buf)
+        return [bytes(mv[o:o + l]) for o, l in zip(offs[:-1].tolist(), out_l[:n].tolist())]
 
     # Prepared calls: the ctypes argument blocks are built once, so a timed region contains only the C ABI calls.
     def prepare_rows(self, ids: Sequence[int], rows: Sequence[bytes], weights: Sequence[float], download_caps: Optional[Sequence[int]] = None):
@@ -263,32 +273,54 @@ class Context:
     def rows_clear(self):
         self._check(self._lib.twl_rows_clear(self._h))
 
+    _SIDE_DT = np.dtype([("seq_ids", "u8"), ("n_ids", "i4"), ("aln_len", "i4"), ("aln_num", "i4"), ("aln_weight", "f4"), ("msa_freq", "u8")])
+    _PAIR_DT = np.dtype([("ref", _SIDE_DT), ("qry", _SIDE_DT), ("flags", "i4"), ("reserved", "i4")])
+    _RES_DT = np.dtype([("status", "i4"), ("path_len", "i4"), ("tiles", "i4"), ("cached", "i4"), ("cells", "u8"), ("diagonals", "u8"),
+                        ("ref_len_dp", "i4"), ("qry_len_dp", "i4")])
+
     def align_level(self, pairs: Sequence[LevelPairIn], task: int = 0, gappy: float = 0.95, cache_threshold: int = 1000) -> List[LevelOut]:
+        """One guide-tree level through twl_align_level. The argument block is assembled with numpy (the structs of
+        include/twilight_b200.h as structured dtypes), not one ctypes object per field."""
         n = len(pairs)
-        arr = (_lib.LevelPair * max(n, 1))()
+        assert self._PAIR_DT.itemsize == C.sizeof(_lib.LevelPair) and self._RES_DT.itemsize == C.sizeof(_lib.LevelResult)
+        arr = np.zeros(max(n, 1), self._PAIR_DT)
+        sides = [sd for p in pairs for sd in (p.ref, p.qry)]
+        meta = np.array([(len(sd.seq_ids), sd.aln_len, sd.aln_num) for sd in sides], np.int64).reshape(2 * n, 3)
+        wts = np.array([sd.aln_weight for sd in sides], np.float32)
+        counts = meta[:, 0]
+        all_ids = np.fromiter((i for sd in sides for i in sd.seq_ids), np.int32, int(counts.sum())) if n else np.zeros(0, np.int32)
+        all_ids = np.concatenate([all_ids, np.zeros(1, np.int32)])                  # never an empty buffer
+        starts = np.concatenate([[0], np.cumsum(counts)])[:-1] if n else np.zeros(0, np.int64)
+        ptr = (all_ids.ctypes.data + 4 * starts).astype(np.uint64)
         keep = []
-        caps = []
-        for k, p in enumerate(pairs):
-            for side, dst in ((p.ref, arr[k].ref), (p.qry, arr[k].qry)):
-                ids = (C.c_int32 * max(len(side.seq_ids), 1))(*[int(i) for i in side.seq_ids])
-                keep.append(ids)
-                dst.seq_ids = ids
-                dst.n_ids = len(side.seq_ids)
-                dst.aln_len, dst.aln_num, dst.aln_weight = int(side.aln_len), int(side.aln_num), float(side.aln_weight)
-                if side.msa_freq is not None:
-                    f = np.ascontiguousarray(side.msa_freq, np.float32)
-                    keep.append(f)
-                    dst.msa_freq = f.ctypes.data
-                else:
-                    dst.msa_freq = None
-            arr[k].flags = 1 if p.profile_only else 0
-            caps.append(p.ref.aln_len + p.qry.aln_len)
-        bufs = [np.zeros(max(c, 1), np.int8) for c in caps]
-        ptrs = (C.c_void_p * max(n, 1))(*[b.ctypes.data for b in bufs])
-        res = (_lib.LevelResult * max(n, 1))()
-        self._check(self._lib.twl_align_level(self._h, arr, n, int(task), float(gappy), int(cache_threshold), ptrs, res))
-        return [LevelOut(res[k].status, bufs[k][:res[k].path_len].copy(), res[k].tiles, int(res[k].cells), bool(res[k].cached & 1),
-                         bool(res[k].cached & 2), bool(res[k].cached & 4), res[k].ref_len_dp, res[k].qry_len_dp) for k in range(n)]
+        freq_ptr = np.zeros(2 * n, np.uint64)
+        for k, sd in enumerate(sides):
+            if sd.msa_freq is not None:
+                f = np.ascontiguousarray(sd.msa_freq, np.float32)
+                keep.append(f)
+                freq_ptr[k] = f.ctypes.data
+        for name, lo in (("ref", 0), ("qry", 1)):
+            v = arr[name][:n]
+            v["seq_ids"] = ptr[lo::2]
+            v["n_ids"] = meta[lo::2, 0]
+            v["aln_len"] = meta[lo::2, 1]
+            v["aln_num"] = meta[lo::2, 2]
+            v["aln_weight"] = wts[lo::2]
+            v["msa_freq"] = freq_ptr[lo::2]
+        arr["flags"][:n] = np.fromiter((1 if p.profile_only else 0 for p in pairs), np.int32, n)
+        caps = (arr["ref"]["aln_len"][:n].astype(np.int64) + arr["qry"]["aln_len"][:n] + 15) & ~15
+        offs = np.concatenate([[0], np.cumsum(caps)]).astype(np.int64)
+        path_buf = np.zeros(int(offs[-1]) + 16, np.int8)
+        ptrs = np.concatenate([(path_buf.ctypes.data + offs[:-1]).astype(np.uint64), np.zeros(1, np.uint64)])
+        res = np.zeros(max(n, 1), self._RES_DT)
+        self._check(self._lib.twl_align_level(self._h, arr.ctypes.data_as(C.POINTER(_lib.LevelPair)), n, int(task), float(gappy), int(cache_threshold),
+                                              ptrs.ctypes.data_as(C.POINTER(C.c_void_p)), res.ctypes.data_as(C.POINTER(_lib.LevelResult))))
+        del keep
+        r = res[:n]
+        st, pl, tl, ce, ca = r["status"].tolist(), r["path_len"].tolist(), r["tiles"].tolist(), r["cells"].tolist(), r["cached"].tolist()
+        rl, ql, oo = r["ref_len_dp"].tolist(), r["qry_len_dp"].tolist(), offs[:-1].tolist()
+        return [LevelOut(st[k], path_buf[oo[k]:oo[k] + pl[k]].copy(), tl[k], ce[k], bool(ca[k] & 1), bool(ca[k] & 2), bool(ca[k] & 4), rl[k], ql[k])
+                for k in range(n)]
 
     def level_fetch(self, pair: int, what: int) -> np.ndarray:
         size = C.c_size_t(0)

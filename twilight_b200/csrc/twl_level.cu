@@ -292,6 +292,12 @@ int twl_rows_length(twl_ctx *ctx, int32_t id) {
     return ctx->level->rows[id].len;
 }
 
+int twl_rows_lengths(twl_ctx *ctx, int n, const int32_t *ids, int32_t *lens) {
+    if (!ctx || n < 0 || (n > 0 && (!ids || !lens))) return TWL_E_ARG;
+    for (int i = 0; i < n; ++i) lens[i] = twl_rows_length(ctx, ids[i]);
+    return TWL_OK;
+}
+
 int twl_rows_download(twl_ctx *ctx, int n, const int32_t *ids, char *const *dst, int32_t *lens) {
     if (!ctx) return TWL_E_ARG;
     if (n < 0 || (n > 0 && (!ids || !dst))) return twlFail(ctx, TWL_E_ARG, "twl_rows_download: null argument");
