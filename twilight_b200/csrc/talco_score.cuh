@@ -74,11 +74,19 @@ __device__ __forceinline__ float numeratorNtPre(const float (&r)[6], const float
 }
 
 // Protein, P = 22; S is the 21x21 matrix.
+// Reference letters with a zero count contribute only exact zeros (every product has the factor r[l] = 0 and is added to
+// a finite sum), so they are skipped: each lane walks the non-zero letters of ITS column in increasing order, which keeps
+// the order of the floating-point sum; a leaf column (one-hot) costs one of 21 iterations, a typical profile column 3-6.
+// The sign of a zero sum may differ from the reference's (-0 vs +0); it cannot reach any comparison or stored value.
 template <typename MatPtr>
 __device__ __forceinline__ float numeratorAa(const float (&r)[22], const float (&q)[22], MatPtr S, float g) {
     float num = 0.0f;
-#pragma unroll 1
-    for (int l = 0; l < 21; ++l) {
+    unsigned live = 0;
+#pragma unroll
+    for (int l = 0; l < 21; ++l) live |= (r[l] != 0.0f ? 1u : 0u) << l;
+    while (live) {
+        const int l = __ffs(live) - 1;
+        live &= live - 1;
         const float rl = r[l];
         float v[8];
 #pragma unroll
