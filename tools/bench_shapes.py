@@ -26,6 +26,8 @@ def batch(n_pairs, length, kind, members, divergence, indel, seed):
 for name, kind, n, L, members, div, indel, score in (
         ("sars-like 30 kb (dna)", "dna", 296, 29700, (1, 2, 4), 0.002, 0.001, None),
         ("protein 400 aa", "protein", 4096, 400, (1, 2, 4, 8), 0.5, 0.02, ol.protein_matrix())):
+    if os.environ.get("SHAPES") and os.environ["SHAPES"] not in name:
+        continue
     ctx = twilight_b200.Context(score=score)
     ids, rows, w, pairs = batch(n, L, kind, members, div, indel, 3)
     for _ in range(2):
@@ -34,5 +36,6 @@ for name, kind, n, L, members, div, indel, score in (
         ph = ctx.level_phase_ms()
     cells = sum(o.cells for o in outs)
     print("%-24s %5d pairs: dp %.2f ms  %.2f GCUPS | all phases %.2f ms | tiles/pair %.1f band %.0f failed %d" % (
-        name, n, ph[2], cells / ph[2] / 1e6, sum(ph), np.mean([o.tiles for o in outs]), cells / max(1, sum(len(o.path) for o in outs)), sum(o.status != 0 for o in outs)))
+        name, n, ph[2], cells / ph[2] / 1e6, sum(ph), np.mean([o.tiles for o in outs]), cells / max(1, sum(len(o.path) for o in outs)), sum(o.status != 0 for o in outs)),
+        "| TWL_OPTIONS=" + os.environ.get("TWL_OPTIONS", ""))
     ctx.close()
