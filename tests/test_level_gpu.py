@@ -168,3 +168,26 @@ def test_coinciding_gappy_runs_are_realigned(ins_len, expect_host):
     assert ctx.rows_download(list(range(48))) == rec.merged.rows
     assert ctx.host_restores() == expect_host
     ctx.close()
+
+
+@pytest.mark.parametrize("seed", list(range(10)))
+def test_level_pipeline_fuzz(seed):
+    """Random small trees with random marker / gappy threshold / indel rate / cache threshold: every stage of every pair
+    against the oracle. Low thresholds make many removed runs (also at column 0 and at the end) and many coinciding run
+    pairs for the consensus re-alignment of the restore kernel."""
+    import twilight_b200
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(5, 14))
+    L = int(rng.integers(60, 500))
+    marker = int(rng.choice([32, 64, 128, 1024]))
+    gappy = float(rng.choice([0.3, 0.5, 0.7, 0.9, 0.95]))
+    cache = int(rng.choice([2, 4, 1000]))
+    tree = synth.random_tree(n, seed=seed, mean_blen=float(rng.uniform(0.03, 0.15)))
+    seqs = synth.evolve(tree, L, seed=seed, indel_rate=float(rng.uniform(0.02, 0.25)))
+    w = rng.uniform(0.5, 1.5, n).astype(np.float32)
+    cfg = ol.TalcoCfg(marker=marker)
+    ctx = twilight_b200.Context(marker=marker)
+    done = run_tree_on_gpu(ctx, tree, seqs, w, cfg, gappy, cache)
+    assert ctx.host_restores() == 0
+    ctx.close()
+    assert done == n - 1
