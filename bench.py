@@ -150,6 +150,33 @@ def run_msa(ctx, n_leaves, length, seed, repeats=3):
             "note": "upper guide-tree levels hold 1-8 pairs and are latency bound (inherent to progressive alignment)"}
 
 
+def run_msa_sharded(ctx, dist, world, n_leaves, length, seed, repeats=3):
+    """N > 1: the same kind of job with world x as many leaves, sharded by subtree over the ranks (no data-path collective;
+    finished child nodes move to the parent's rank where a join crosses ranks). Every rank calls this; wall clock is the max
+    over ranks between two barriers."""
+    import torch
+    from twilight_b200 import msa, synth
+    tree = synth.random_tree(n_leaves, seed=seed, mean_blen=0.05)
+    seqs = synth.evolve(tree, length, seed=seed, kind="rna")
+    w = np.ones(n_leaves, np.float32)
+    best, keep = None, None
+    for _ in range(repeats):
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rows, st, root_owner = msa.progressive_align_sharded(ctx, tree, seqs, w, dist)
+        dist.barrier(); torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if best is None or dt < best:
+            best, keep = dt, st
+    v = torch.tensor([best, keep.device_ms, float(keep.cells), float(keep.pairs)], dtype=torch.float64, device="cuda")
+    mx = v.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    sm = v.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    wall = float(mx[0])
+    return {"leaves": n_leaves, "root_len": length, "ranks": world, "pairs": int(sm[3]), "cells": int(sm[2]), "wall_s": wall,
+            "seqs_per_s_e2e": n_leaves / wall, "device_ms_max_rank": float(mx[1]),
+            "note": "sharded by subtree (twilight_b200/shard.py); rows of a finished child move between ranks only at the top joins"}
+
+
 def run_reference_arm(args):
     """--impl reference: the reference's own CPU implementation of the path on the host cores, same workload generator,
     metric and unit as the B200 arm; each step is a bounded sample of the level (4 pairs per host thread)."""
@@ -294,6 +321,10 @@ def main():
     else:
         dev_all, e2e_all, cells_all = dev_total, e2e_total, float(cells)
 
+    msa_sharded = None
+    if dist is not None and args.msa_leaves > 0:
+        msa_sharded = run_msa_sharded(ctx, dist, world, args.msa_leaves * world, args.length, seed=77)
+
     if rank == 0:
         pk = peaks()
         gcups = cells_all * args.steps / (dev_all * 1e-3) / 1e9
@@ -336,6 +367,8 @@ def main():
             for name, b, ms in (("profile_build", prof_bytes, phases[0]), ("gappy_psgp_pack", pack_bytes, phases[1]), ("row_update", upd_bytes, phases[3]))}
         if args.msa_leaves > 0:
             line["msa"] = run_msa(ctx, args.msa_leaves, args.length, seed=77)
+        if msa_sharded is not None:
+            line["msa_sharded"] = msa_sharded
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             n_sample = max(threads, min(len(pairs), 16 * threads))
