@@ -99,6 +99,13 @@ int twl_batch_fetch(twl_ctx *ctx, int8_t *const *paths, twl_pair_result *results
  *      (SequenceInfo::id). ------------------------------------------------------------------------------------- */
 int twl_rows_upload(twl_ctx *ctx, int n, const int32_t *ids, const char *const *rows, const int32_t *lens, const float *weights);
 int twl_rows_download(twl_ctx *ctx, int n, const int32_t *ids, char *const *dst, int32_t *lens);   /* dst[i] holds >= current length */
+/* Multi-GPU node migration without a host bounce: pack the current text of n rows into one contiguous
+ * DEVICE buffer (row i at offsets[i], 16-byte aligned, offsets returned to the host) so it can be sent to another rank
+ * over NVLink (NCCL send/recv, cudaMemcpyPeer), and create / overwrite n rows from such a buffer on the receiving context.
+ * dev_dst must hold sum(align16(len)) bytes; both calls return with the work complete on the context's stream. */
+int twl_rows_export(twl_ctx *ctx, int n, const int32_t *ids, void *dev_dst, size_t cap_bytes, int32_t *lens, int64_t *offsets);
+int twl_rows_import(twl_ctx *ctx, int n, const int32_t *ids, const int32_t *lens, const float *weights, const void *dev_src,
+                    const int64_t *offsets);
 int twl_rows_length(twl_ctx *ctx, int32_t id);
 /* The same for n rows at once: lens[i] = current length of row ids[i], or -1. */
 int twl_rows_lengths(twl_ctx *ctx, int n, const int32_t *ids, int32_t *lens);   /* current length of a row, <0 if unknown */

@@ -55,6 +55,8 @@ SIGNATURES = {
     "twl_batch_fetch": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(PairResult)]),
     "twl_rows_upload": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_char_p), C.POINTER(C.c_int32), C.POINTER(C.c_float)]),
     "twl_rows_download": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
+    "twl_rows_export": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_void_p, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
+    "twl_rows_import": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float), C.c_void_p, C.POINTER(C.c_int64)]),
     "twl_rows_length": (C.c_int, [C.c_void_p, C.c_int32]),
     "twl_rows_lengths": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "twl_rows_clear": (C.c_int, [C.c_void_p]),

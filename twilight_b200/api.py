@@ -214,6 +214,26 @@ class Context:
         mv = memoryview(buf)
         return [bytes(mv[o:o + l]) for o, l in zip(offs[:-1].tolist(), out_l[:n].tolist())]
 
+    def rows_export(self, ids: Sequence[int], dev_ptr: int, cap_bytes: int):
+        """Packs rows into a contiguous DEVICE buffer (twl_rows_export). Returns (lens, offsets) as numpy arrays."""
+        n = len(ids)
+        a_ids = np.asarray(ids, np.int32)
+        lens = np.zeros(max(n, 1), np.int32)
+        offs = np.zeros(max(n, 1), np.int64)
+        self._check(self._lib.twl_rows_export(self._h, n, a_ids.ctypes.data_as(C.POINTER(C.c_int32)), C.c_void_p(dev_ptr), int(cap_bytes),
+                                              lens.ctypes.data_as(C.POINTER(C.c_int32)), offs.ctypes.data_as(C.POINTER(C.c_int64))))
+        return lens[:n], offs[:n]
+
+    def rows_import(self, ids: Sequence[int], lens, weights, dev_ptr: int, offsets):
+        """Creates / overwrites rows from a contiguous DEVICE buffer (twl_rows_import)."""
+        n = len(ids)
+        a_ids = np.asarray(ids, np.int32)
+        a_l = np.ascontiguousarray(lens, np.int32)
+        a_w = np.ascontiguousarray(weights, np.float32)
+        a_o = np.ascontiguousarray(offsets, np.int64)
+        self._check(self._lib.twl_rows_import(self._h, n, a_ids.ctypes.data_as(C.POINTER(C.c_int32)), a_l.ctypes.data_as(C.POINTER(C.c_int32)),
+                                              a_w.ctypes.data_as(C.POINTER(C.c_float)), C.c_void_p(dev_ptr), a_o.ctypes.data_as(C.POINTER(C.c_int64))))
+
     # Prepared calls: the ctypes argument blocks are built once, so a timed region contains only the C ABI calls.
     def prepare_rows(self, ids: Sequence[int], rows: Sequence[bytes], weights: Sequence[float], download_caps: Optional[Sequence[int]] = None):
         n = len(ids)

@@ -292,6 +292,63 @@ int twl_rows_length(twl_ctx *ctx, int32_t id) {
     return ctx->level->rows[id].len;
 }
 
+int twl_rows_export(twl_ctx *ctx, int n, const int32_t *ids, void *dev_dst, size_t cap_bytes, int32_t *lens, int64_t *offsets) {
+    if (!ctx) return TWL_E_ARG;
+    if (n < 0 || (n > 0 && (!ids || !dev_dst || !lens || !offsets))) return twlFail(ctx, TWL_E_ARG, "twl_rows_export: null argument");
+    TwlLevelState *L = levelOf(ctx);
+    cudaSetDevice(ctx->device);
+    if (n == 0) return TWL_OK;
+    std::vector<twl::RowCopy> list(n);
+    size_t total = 0;
+    for (int i = 0; i < n; ++i) {
+        if (ids[i] < 0 || static_cast<size_t>(ids[i]) >= L->rows.size() || !L->rows[ids[i]].present)
+            return twlFail(ctx, TWL_E_ARG, "twl_rows_export: unknown row id " + std::to_string(ids[i]));
+        const RowSlot &r = L->rows[ids[i]];
+        list[i].dev = r.buf[r.storage]; list[i].stageOff = static_cast<long long>(total); list[i].len = r.len; list[i].pad = 0;
+        lens[i] = r.len; offsets[i] = static_cast<int64_t>(total);
+        total += (static_cast<size_t>(r.len) + 15) & ~static_cast<size_t>(15);
+    }
+    if (total > cap_bytes) return twlFail(ctx, TWL_E_ARG, "twl_rows_export: destination too small");
+    if (L->stagePending) { TWL_CUDA(ctx, cudaEventSynchronize(L->stageFree)); L->stagePending = false; }
+    TWL_CUDA(ctx, L->dCopies.reserve(n));
+    TWL_CUDA(ctx, cudaMemcpyAsync(L->dCopies.ptr, list.data(), sizeof(twl::RowCopy) * n, cudaMemcpyHostToDevice, ctx->stream));
+    twl::rowTransferKernel<<<(n * 32 + 255) / 256, 256, 0, ctx->stream>>>(L->dCopies.ptr, n, static_cast<char *>(dev_dst), 0);
+    TWL_CUDA(ctx, cudaGetLastError());
+    TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TWL_OK;
+}
+
+int twl_rows_import(twl_ctx *ctx, int n, const int32_t *ids, const int32_t *lens, const float *weights, const void *dev_src,
+                    const int64_t *offsets) {
+    if (!ctx) return TWL_E_ARG;
+    if (n < 0 || (n > 0 && (!ids || !lens || !weights || !dev_src || !offsets))) return twlFail(ctx, TWL_E_ARG, "twl_rows_import: null argument");
+    TwlLevelState *L = levelOf(ctx);
+    cudaSetDevice(ctx->device);
+    if (n == 0) return TWL_OK;
+    std::vector<twl::RowCopy> list(n);
+    for (int i = 0; i < n; ++i) {
+        if (ids[i] < 0 || lens[i] < 0 || offsets[i] < 0) return twlFail(ctx, TWL_E_ARG, "twl_rows_import: negative id, length or offset");
+        const int id = ids[i];
+        if (static_cast<size_t>(id) >= L->rows.size()) L->rows.resize(id + 1);
+        RowSlot &r = L->rows[id];
+        const int cap = std::max(16, 2 * lens[i]);
+        if (!r.present || r.cap < lens[i]) {
+            TWL_CUDA(ctx, poolAlloc(L, cap, &r.buf[0]));
+            TWL_CUDA(ctx, poolAlloc(L, cap, &r.buf[1]));
+            r.cap = cap;
+        }
+        r.len = lens[i]; r.storage = 0; r.weight = weights[i]; r.present = true;
+        list[i].dev = r.buf[0]; list[i].stageOff = static_cast<long long>(offsets[i]); list[i].len = lens[i]; list[i].pad = 0;
+    }
+    if (L->stagePending) { TWL_CUDA(ctx, cudaEventSynchronize(L->stageFree)); L->stagePending = false; }
+    TWL_CUDA(ctx, L->dCopies.reserve(n));
+    TWL_CUDA(ctx, cudaMemcpyAsync(L->dCopies.ptr, list.data(), sizeof(twl::RowCopy) * n, cudaMemcpyHostToDevice, ctx->stream));
+    twl::rowTransferKernel<<<(n * 32 + 255) / 256, 256, 0, ctx->stream>>>(L->dCopies.ptr, n, const_cast<char *>(static_cast<const char *>(dev_src)), 1);
+    TWL_CUDA(ctx, cudaGetLastError());
+    TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TWL_OK;
+}
+
 int twl_rows_lengths(twl_ctx *ctx, int n, const int32_t *ids, int32_t *lens) {
     if (!ctx || n < 0 || (n > 0 && (!ids || !lens))) return TWL_E_ARG;
     for (int i = 0; i < n; ++i) lens[i] = twl_rows_length(ctx, ids[i]);

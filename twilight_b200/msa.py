@@ -108,18 +108,47 @@ def progressive_align_sharded(ctx, tree: synth.Tree, seqs: Sequence[bytes], weig
         # nodes that finish on one rank and are consumed on another
         moving = [(c, int(owner[c]), int(owner[p])) for a, b, p in level for c in (a, b) if owner[c] != owner[p]]
         if moving:
-            out = {}
-            for c, src, dst in moving:
-                if src == rank:
-                    nb = book.pop(c)
-                    out[c] = (dst, nb, ctx.rows_download(nb.ids), [float(w) for w in np.asarray(weights)[nb.ids]])
-            gathered = [None] * world
-            dist.all_gather_object(gathered, out)
-            for part in gathered:
-                for c, (dst, nb, rows, w) in part.items():
-                    if dst == rank:
-                        ctx.rows_upload(nb.ids, rows, w)
+            device_path = hasattr(ctx, "rows_export") and dist.get_backend() == "nccl"
+            if device_path:
+                # rows travel GPU -> GPU (NCCL send/recv over NVLink) in one packed device buffer per node; only the node's
+                # bookkeeping (ids, lengths, weights, cached msaFreq) goes through the object collective
+                import torch
+                out = {}
+                for c, src, dst in moving:
+                    if src == rank:
+                        nb = book[c]
+                        out[c] = (dst, nb, [float(w) for w in np.asarray(weights)[nb.ids]])
+                gathered = [None] * world
+                dist.all_gather_object(gathered, out)
+                meta = {c: v for part in gathered for c, v in part.items()}
+                for c, src, dst in moving:
+                    _, nb, w = meta[c]
+                    total = len(nb.ids) * ((nb.aln_len + 15) & ~15)
+                    if src == rank:
+                        buf = torch.empty(max(total, 16), dtype=torch.uint8, device="cuda")
+                        ctx.rows_export(nb.ids, buf.data_ptr(), buf.numel())
+                        dist.send(buf, dst)
+                        book.pop(c)
+                    elif dst == rank:
+                        buf = torch.empty(max(total, 16), dtype=torch.uint8, device="cuda")
+                        dist.recv(buf, src)
+                        lens = np.full(len(nb.ids), nb.aln_len, np.int32)
+                        offs = np.arange(len(nb.ids), dtype=np.int64) * ((nb.aln_len + 15) & ~15)
+                        ctx.rows_import(nb.ids, lens, w, buf.data_ptr(), offs)
                         book[c] = nb
+            else:
+                out = {}
+                for c, src, dst in moving:
+                    if src == rank:
+                        nb = book.pop(c)
+                        out[c] = (dst, nb, ctx.rows_download(nb.ids), [float(w) for w in np.asarray(weights)[nb.ids]])
+                gathered = [None] * world
+                dist.all_gather_object(gathered, out)
+                for part in gathered:
+                    for c, (dst, nb, rows, w) in part.items():
+                        if dst == rank:
+                            ctx.rows_upload(nb.ids, rows, w)
+                            book[c] = nb
         todo = [(a, b, p) for a, b, p in level if owner[p] == rank]
         if not todo:
             continue
