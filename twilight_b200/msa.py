@@ -132,6 +132,7 @@ def progressive_align_sharded(ctx, tree: synth.Tree, seqs: Sequence[bytes], weig
                     elif dst == rank:
                         buf = torch.empty(max(total, 16), dtype=torch.uint8, device="cuda")
                         dist.recv(buf, src)
+                        torch.cuda.current_stream().synchronize()    # the import runs on the context's own stream
                         lens = np.full(len(nb.ids), nb.aln_len, np.int32)
                         offs = np.arange(len(nb.ids), dtype=np.int64) * ((nb.aln_len + 15) & ~15)
                         ctx.rows_import(nb.ids, lens, w, buf.data_ptr(), offs)
