@@ -48,3 +48,14 @@ def test_product_package_does_not_touch_the_oracle():
                 text = open(os.path.join(base, f), errors="ignore").read()
                 hit = bad.search(text)
                 assert hit is None, f"{os.path.join(base, f)}: {hit.group(0)}"
+
+
+def test_numpy_struct_mirrors_match_ctypes():
+    """The Python mirror assembles twl_level_pair / twl_level_result blocks as numpy structured arrays: their layout must
+    equal the ctypes (= C header) structs field by field."""
+    import ctypes as C
+    from twilight_b200 import _lib, api
+    for dt, st in ((api.Context._SIDE_DT, _lib.NodeSide), (api.Context._PAIR_DT, _lib.LevelPair), (api.Context._RES_DT, _lib.LevelResult)):
+        assert dt.itemsize == C.sizeof(st)
+        for name, _ in st._fields_:
+            assert dt.fields[name][1] == getattr(st, name).offset, name
