@@ -115,3 +115,40 @@ def test_port_frequency_cache_and_merge_equal_reference():
     assert np.array_equal(rec2.profile_raw[0], want2["profile_raw"][0])
     assert np.array_equal(rec2.aln_w, want2["aln_w"])
     assert np.array_equal(rec2.merged.msa_freq, want2["merged"])
+
+
+@needs_ref
+@pytest.mark.parametrize("ins_len", [3, 25, 150])
+def test_port_coinciding_gappy_runs_equal_reference(ins_len):
+    """Removed runs of both nodes that start at the same path position (addGappyColumnsBack + pairwiseGlobal,
+    alignment-helper.cpp:324-375, 243-322): the crafted case of tests/test_level_gpu.py, port against the unmodified
+    reference helpers."""
+    import copy
+    rng = np.random.default_rng(5)
+    letters = np.frombuffer(b"ACGU", np.uint8)
+    anc = rng.choice(letters, 500)
+
+    def family(seed, members):
+        r = np.random.default_rng(seed)
+        ins = r.choice(letters, ins_len)
+        rows = []
+        for m in range(members):
+            row = anc.copy()
+            flip = r.random(row.size) < 0.03
+            row[flip] = r.choice(letters, int(flip.sum()))
+            mid = ins if m == 0 else np.full(ins_len, ord("-"), np.uint8)
+            rows.append(np.concatenate([row[:250], mid, row[250:]]).tobytes())
+        return rows
+
+    ra, rb = family(1, 24), family(2, 24)
+    L = len(ra[0])
+    w = np.ones(24, np.float32)
+    cfg = ol.TalcoCfg()
+    sa, sb = ref_msa.NodeState(ra, w, L, 24, 24.0), ref_msa.NodeState(rb, w.copy(), L, 24, 24.0)
+    want = ol.ref_pipeline("n", cfg, copy.deepcopy(sa), copy.deepcopy(sb), 0.9)
+    rec = ref_msa.align_pair("n", cfg, sa, sb, 0.9)
+    assert len(rec.runs[0]) >= 1 and len(rec.runs[1]) >= 1
+    assert rec.error == want["error"] == 0
+    assert np.array_equal(rec.aln_wo, want["aln_wo"])
+    assert np.array_equal(rec.aln_w, want["aln_w"])
+    assert rec.merged.rows == want["new_rows"]
