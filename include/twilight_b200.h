@@ -170,9 +170,10 @@ int twl_level_phase_ms(twl_ctx *ctx, float out[4]);
 
 /* addGappyColumnsBack (alignment-helper.cpp:324-375) runs on the device. When removed runs of BOTH nodes start at the same
  * path position the reference aligns their consensus substrings (pairwiseGlobal, alignment-helper.cpp:243-322); the kernel
- * keeps that small alignment in shared memory, and a run pair of more than 8192 matrix cells is redone by the library on the
- * host. Returns how many pairs took that route since twl_init (diagnostics; expected 0 on ordinary data). */
-int twl_level_host_restores(const twl_ctx *ctx);
+ * keeps that alignment in shared memory, and a pair with a run pair of more than 8192 matrix cells is redone by a second
+ * pass of the same kernel with its matrices in a global scratch buffer. Returns how many pairs took the second pass since
+ * twl_init (diagnostics; 0 on ordinary data). */
+int twl_level_large_restores(const twl_ctx *ctx);
 
 /* Device time (CUDA events on the context's stream) of the kernels of the last run(), in milliseconds, and the number
  * of kernel launches it issued. */

@@ -46,7 +46,7 @@ def test_bench_level_properties_and_determinism():
         prows = ctx.prepare_rows(ids, rows_in, weights, [caps[i] for i in ids])
         plevel = ctx.prepare_level(pairs)
         paths, rows_out = _run(ctx, prows, plevel)
-        assert ctx.host_restores() == 0
+        assert ctx.large_restores() == 0
         ctx.close()
         digests.append(_digest(paths, rows_out))
         if len(digests) > 1:

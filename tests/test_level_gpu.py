@@ -129,11 +129,12 @@ def test_level_is_chunked_transparently(monkeypatch):
     assert st_b.launches > st_a.launches
 
 
-@pytest.mark.parametrize("ins_len,expect_host", [(25, 0), (150, 1)])
-def test_coinciding_gappy_runs_are_realigned(ins_len, expect_host):
+@pytest.mark.parametrize("ins_len,expect_large", [(25, 0), (150, 1), (1300, 1)])
+def test_coinciding_gappy_runs_are_realigned(ins_len, expect_large):
     """Removed runs of both nodes that start at the same path position are aligned against each other (pairwiseGlobal,
-    alignment-helper.cpp:243-322): in the restore kernel's shared memory when small, by the library's host redo when the
-    matrix exceeds it. Same final path and rows as the oracle either way."""
+    alignment-helper.cpp:243-322): in the restore kernel's shared memory when small, by a second pass of the same kernel
+    with global scratch when the matrix exceeds it (150: by cells; 1300: also by row length). Same final path and rows as
+    the oracle either way."""
     import twilight_b200
     rng = np.random.default_rng(5)
     letters = np.frombuffer(b"ACGU", np.uint8)
@@ -166,7 +167,7 @@ def test_coinciding_gappy_runs_are_realigned(ins_len, expect_host):
     assert out.status == rec.error == 0
     assert np.array_equal(out.path, rec.aln_w)
     assert ctx.rows_download(list(range(48))) == rec.merged.rows
-    assert ctx.host_restores() == expect_host
+    assert ctx.large_restores() == expect_large
     ctx.close()
 
 
@@ -188,7 +189,7 @@ def test_level_pipeline_fuzz(seed):
     cfg = ol.TalcoCfg(marker=marker)
     ctx = twilight_b200.Context(marker=marker)
     done = run_tree_on_gpu(ctx, tree, seqs, w, cfg, gappy, cache)
-    assert ctx.host_restores() == 0
+    assert ctx.large_restores() == 0
     ctx.close()
     assert done == n - 1
 

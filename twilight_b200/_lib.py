@@ -63,7 +63,7 @@ SIGNATURES = {
     "twl_align_level": (C.c_int, [C.c_void_p, C.POINTER(LevelPair), C.c_int, C.c_int, C.c_float, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(LevelResult)]),
     "twl_level_fetch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "twl_level_phase_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
-    "twl_level_host_restores": (C.c_int, [C.c_void_p]),
+    "twl_level_large_restores": (C.c_int, [C.c_void_p]),
     "twl_last_kernel_ms": (C.c_float, [C.c_void_p]),
     "twl_last_launch_count": (C.c_int, [C.c_void_p]),
     "twl_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),

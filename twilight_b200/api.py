@@ -121,8 +121,8 @@ class Context:
         if rc != 0:
             raise TwilightError(f"{_lib.ERRORS.get(rc, rc)}: {self._lib.twl_last_error(self._h).decode()}")
 
-    def host_restores(self) -> int:
-        return int(self._lib.twl_level_host_restores(self._h))
+    def large_restores(self) -> int:
+        return int(self._lib.twl_level_large_restores(self._h))
 
     def set_option(self, name: str, value: int):
         self._check(self._lib.twl_set_option(self._h, name.encode(), int(value)))

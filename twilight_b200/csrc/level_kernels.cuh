@@ -269,8 +269,8 @@ __global__ void __launch_bounds__(kLvlThreads) gappyCompactKernel(DevSide *sides
 // original coordinate reaches the run's start; runs hit on both sides at the same op are aligned against each other by a
 // small affine-gap global alignment of the two consensus substrings). One warp per pair, lane 0 walks; the walk costs
 // ~0.1-0.2 ms per pair and thousands of pairs walk concurrently, so the phase is invisible next to the DP.
-// The consensus alignment keeps its matrices in shared memory; a run pair too large for them raises needHost and the
-// library redoes that pair's restore on the host (rare: both runs must be long and start at the same op).
+// The consensus alignment keeps its matrices in shared memory; a pair with a run pair too large for them is redone by the
+// LARGE instantiation of the same kernel (matrices in global scratch), see below.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kRestoreTbCells = 8192;       // (m+1)*(n+1) limit of the in-kernel consensus alignment
 constexpr int kRestoreRowCap = 1024;        // n+1 limit
@@ -282,34 +282,34 @@ constexpr int kRestoreRowCap = 1024;        // n+1 limit
 // returns len (same value in every lane).
 __device__ __forceinline__ int consensusAlignWarp(int lane, const char *s1, int m, const char *s2, int n, const float *sScore, int M, int isProtein,
                                                   const signed char *aaLut, float gapOpen, float gapExtend, int8_t *tb,
-                                                  float (*rM)[kRestoreRowCap], float (*rX)[kRestoreRowCap], float (*rY)[kRestoreRowCap],
-                                                  unsigned char *idx2, int8_t *out) {
-    const int W = n + 1;
+                                                  float *rM, float *rX, float *rY, int rowStride, unsigned char *idx2, int8_t *out) {
+    const size_t W = static_cast<size_t>(n) + 1;
     const float big = -1e9f;
     for (int t = lane; t < n; t += 32) { const unsigned char c = static_cast<unsigned char>(s2[t]); idx2[t] = static_cast<unsigned char>(isProtein ? letterIndexAa(c, aaLut) : letterIndexNt(c)); }
-    for (int j = lane; j <= n; j += 32) { rM[0][j] = 0.0f; rX[0][j] = (j > 0) ? big : 0.0f; rY[0][j] = 0.0f; }
+    for (int j = lane; j <= n; j += 32) { rM[j] = 0.0f; rX[j] = (j > 0) ? big : 0.0f; rY[j] = 0.0f; }
     __syncwarp();
     for (int i = 1; i <= m; ++i) {
-        const int cur = i & 1, prv = cur ^ 1;
+        float *cM = rM + (i & 1) * rowStride, *cX = rX + (i & 1) * rowStride, *cY = rY + (i & 1) * rowStride;
+        const float *pM = rM + ((i & 1) ^ 1) * rowStride, *pX = rX + ((i & 1) ^ 1) * rowStride, *pY = rY + ((i & 1) ^ 1) * rowStride;
         const unsigned char c1 = static_cast<unsigned char>(s1[i - 1]);
         const float *srow = sScore + (isProtein ? letterIndexAa(c1, aaLut) : letterIndexNt(c1)) * M;
         for (int j = 1 + lane; j <= n; j += 32) {
-            rM[cur][j] = __fadd_rn(srow[idx2[j - 1]], fmaxf(fmaxf(rM[prv][j - 1], rX[prv][j - 1]), rY[prv][j - 1]));
-            rX[cur][j] = fmaxf(__fadd_rn(rM[prv][j], gapOpen), __fadd_rn(rX[prv][j], gapExtend));
+            cM[j] = __fadd_rn(srow[idx2[j - 1]], fmaxf(fmaxf(pM[j - 1], pX[j - 1]), pY[j - 1]));
+            cX[j] = fmaxf(__fadd_rn(pM[j], gapOpen), __fadd_rn(pX[j], gapExtend));
         }
-        if (lane == 0) { rM[cur][0] = 0.0f; rX[cur][0] = 0.0f; rY[cur][0] = big; }
+        if (lane == 0) { cM[0] = 0.0f; cX[0] = 0.0f; cY[0] = big; }
         __syncwarp();
         if (lane == 0) {
             float y = big;
 #pragma unroll 4
             for (int j = 1; j <= n; ++j) {
-                y = fmaxf(__fadd_rn(rM[cur][j - 1], gapOpen), __fadd_rn(y, gapExtend));
-                rY[cur][j] = y;
+                y = fmaxf(__fadd_rn(cM[j - 1], gapOpen), __fadd_rn(y, gapExtend));
+                cY[j] = y;
             }
         }
         __syncwarp();
         for (int j = 1 + lane; j <= n; j += 32) {
-            const float vm = rM[cur][j], vx = rX[cur][j], vy = rY[cur][j];
+            const float vm = cM[j], vx = cX[j], vy = cY[j];
             const float best = fmaxf(fmaxf(vm, vx), vy);
             tb[i * W + j] = (best == vm) ? 0 : ((best == vy) ? 1 : 2);
         }
@@ -332,31 +332,51 @@ __device__ __forceinline__ int consensusAlignWarp(int lane, const char *s1, int 
     return __shfl_sync(0xffffffffu, len, 0);
 }
 
-__global__ void __launch_bounds__(32) gappyRestoreKernel(DevUpdate *ups, const int *updPair, int nu, const DevPair *pairs, DevResult *results,
-                                                         const DevSide *sides, const int *runs, const char *cons, int8_t *pathsWo,
+// LARGE = false: the consensus alignment lives in shared memory; a coinciding run pair that does not fit makes the kernel
+// finish the walk without writing (it only records the largest matrix and row it would need in `need`) and the pair is
+// redone by the LARGE = true instantiation, whose matrices live in a per-block slice of a global scratch buffer sized by
+// the host from `need`. Same code, same bits; only where the scratch is differs.
+template <bool LARGE>
+__global__ void __launch_bounds__(32) gappyRestoreKernel(DevUpdate *ups, const int *updPair, const int *which, int nu, const DevPair *pairs,
+                                                         DevResult *results, const DevSide *sides, const int *runs, const char *cons, int8_t *pathsWo,
                                                          int8_t *finalPaths, const float *score, int M, int isProtein, const signed char *aaLut,
-                                                         float gapOpen, float gapExtend, int *needHost) {
-    __shared__ int8_t tb[kRestoreTbCells];
-    __shared__ float dM[2][kRestoreRowCap], dX[2][kRestoreRowCap], dY[2][kRestoreRowCap];
+                                                         float gapOpen, float gapExtend, long long *need, char *largeScratch,
+                                                         long long largeCells, int largeCols) {
+    constexpr int kTb = LARGE ? 16 : kRestoreTbCells, kRow = LARGE ? 4 : kRestoreRowCap;
+    __shared__ int8_t sTb[kTb];
+    __shared__ float sM[2 * kRow], sX[2 * kRow], sY[2 * kRow];
+    __shared__ unsigned char sIdx2[kRow];
+    // scratch of the consensus alignment: shared memory, or this block's slice of the global buffer
+    // (slice layout: tb[largeCells] | M,X,Y [2][largeCols] floats each | idx2[largeCols])
+    const long long cellCap = LARGE ? largeCells : kRestoreTbCells;
+    const int colCap = LARGE ? largeCols : kRestoreRowCap;
+    char *slice = LARGE ? largeScratch + static_cast<size_t>(blockIdx.x) * (static_cast<size_t>(largeCells) + 25ull * largeCols + 64) : nullptr;
+    int8_t *tb = LARGE ? reinterpret_cast<int8_t *>(slice) : sTb;
+    float *dM = LARGE ? reinterpret_cast<float *>(slice + ((largeCells + 15) & ~15ll)) : sM;
+    float *dX = LARGE ? dM + 2 * static_cast<size_t>(largeCols) : sX;
+    float *dY = LARGE ? dX + 2 * static_cast<size_t>(largeCols) : sY;
+    unsigned char *idx2 = LARGE ? reinterpret_cast<unsigned char *>(dY + 2 * static_cast<size_t>(largeCols)) : sIdx2;
     // staged windows of the two run lists and of the path: the walk is a chain of dependent reads, which must not each
     // pay a trip to L2
     constexpr int kRunWin = 256, kOpWin = 1024;
     __shared__ int sRunR[2 * kRunWin], sRunQ[2 * kRunWin];
     __shared__ __align__(16) int8_t sOps[kOpWin];
-    __shared__ unsigned char sIdx2[kRestoreRowCap];
     __shared__ float sScore[21 * 21];
     const int lane = threadIdx.x;
     for (int t = lane; t < M * M; t += 32) sScore[t] = score[t];
     __syncwarp();
     // every lane keeps the (uniform) walk state; lane-parallel parts: op copies, run fills, the consensus alignment
-    for (int k = blockIdx.x; k < nu; k += gridDim.x) {
+    for (int kk = blockIdx.x; kk < nu; kk += gridDim.x) {
+        const int k = which ? which[kk] : kk;               // entry of the update list (the LARGE pass lists the pairs to redo)
         const int p = updPair[k];
         DevResult res = results[p];
         const DevPair pr = pairs[p];
         const DevSide sr = sides[2 * p], sq = sides[2 * p + 1];
         int8_t *aln = pathsWo + pr.alnOff;
         __syncwarp();
-        if (lane == 0) needHost[k] = 0;
+        if (lane == 0) { need[2 * k] = 0; need[2 * k + 1] = 0; }
+        long long wantCells = 0;
+        int wantCols = 0;
         if (res.status == kStatusEmptySide) {               // alignment-cpu.cpp:89-90: the other side's columns against nothing
             const int n = (pr.refLen < 1) ? max(pr.qryLen, 0) : max(pr.refLen, 0);
             const int8_t op = (pr.refLen < 1) ? 1 : 2;
@@ -396,18 +416,24 @@ __global__ void __launch_bounds__(32) gappyRestoreKernel(DevUpdate *ups, const i
             const bool hitR = (r == nextR), hitQ = (q == nextQ);
             if (hitR && hitQ) {
                 const int m = sRunR[2 * (gr - baseR) + 1], n = sRunQ[2 * (gq - baseQ) + 1];
-                if (static_cast<long long>(m + 1) * (n + 1) > kRestoreTbCells || n + 1 > kRestoreRowCap) { giveUp = true; break; }
-                w += consensusAlignWarp(lane, consR + r, m, consQ + q, n, sScore, M, isProtein, aaLut, gapOpen, gapExtend, tb, dM, dX, dY, sIdx2, out + w);
+                const long long cells = static_cast<long long>(m + 1) * (n + 1);
+                if (cells > cellCap || n + 1 > colCap) {     // does not fit: finish the walk dry to learn the largest need
+                    giveUp = true;
+                    wantCells = max(wantCells, cells);
+                    wantCols = max(wantCols, n + 1);
+                }
+                if (!giveUp) w += consensusAlignWarp(lane, consR + r, m, consQ + q, n, sScore, M, isProtein, aaLut, gapOpen, gapExtend, tb, dM, dX, dY,
+                                                     colCap, idx2, out + w);
                 r += m; q += n;
             } else {
                 if (hitR) {
                     const int len = sRunR[2 * (gr - baseR) + 1];
-                    for (int t = lane; t < len; t += 32) out[w + t] = 2;
+                    if (!giveUp) for (int t = lane; t < len; t += 32) out[w + t] = 2;
                     w += len; r += len;
                 }
                 if (hitQ) {
                     const int len = sRunQ[2 * (gq - baseQ) + 1];
-                    for (int t = lane; t < len; t += 32) out[w + t] = 1;
+                    if (!giveUp) for (int t = lane; t < len; t += 32) out[w + t] = 1;
                     w += len; q += len;
                 }
             }
@@ -433,7 +459,7 @@ __global__ void __launch_bounds__(32) gappyRestoreKernel(DevUpdate *ups, const i
             const bool hitHere = (lane > 0) && (lane < left) && ((r + __popc(maskR & below) == nextR) || (q + __popc(maskQ & below) == nextQ));
             const unsigned hits = __ballot_sync(0xffffffffu, hitHere);
             const int take = hits ? (__ffs(hits) - 1) : left;      // >= 1
-            if (lane < take) out[w + lane] = static_cast<int8_t>(op);
+            if (lane < take && !giveUp) out[w + lane] = static_cast<int8_t>(op);
             const unsigned upto = (take >= 32) ? 0xffffffffu : ((1u << take) - 1u);
             r += __popc(maskR & upto);
             q += __popc(maskQ & upto);
@@ -441,7 +467,7 @@ __global__ void __launch_bounds__(32) gappyRestoreKernel(DevUpdate *ups, const i
         }
         __syncwarp();
         if (lane == 0) {
-            if (giveUp) { needHost[k] = 1; ups[k].pathLen = 0; }
+            if (giveUp) { need[2 * k] = wantCells; need[2 * k + 1] = wantCols; ups[k].pathLen = 0; }
             else ups[k].pathLen = w;
         }
     }

@@ -47,15 +47,17 @@ struct TwlLevelState {
     DevBuf<int8_t> dFinalPaths;
     DevBuf<signed char> dAaLut;
     DevBuf<twl::DevUpdate> dUps2;
-    DevBuf<int> dUpdPair, dNeedHost;
+    DevBuf<int> dUpdPair, dWhich;
+    DevBuf<long long> dNeed;
+    DevBuf<char> dLargeScratch;
     DevBuf<const char *> dUpdIn;
     PinBuf<twl::DevResult> hRes;
     PinBuf<twl::DevUpdate> hUps;
-    PinBuf<int> hNeedHost;
+    PinBuf<long long> hNeed;
     PinBuf<int8_t> hFinal;
     PinBuf<twl::DevSide> hSides;
     PinBuf<float> hFreqPin, hMergedPin;
-    int hostRestores = 0;        // pairs whose gappy-column restore fell back to the host since the context was created
+    int largeRestores = 0;       // pairs whose gappy-column restore needed the global-scratch pass since the context was created
     DevBuf<twl::RowCopy> dCopies;
     DevBuf<char> dStage;
     PinBuf<char> hStage;
@@ -137,10 +139,7 @@ cudaError_t poolAlloc(TwlLevelState *L, size_t bytes, char **out) {
     return cudaSuccess;
 }
 
-// ---- addGappyColumnsBack + pairwiseGlobal (src/alignment-helper.cpp:324-375, 243-322): O(path) serial merge of the
-// removed-run lists back into the DP path; runs removed on both sides at the same point are aligned against each other by
-// a small affine-gap global alignment of the two consensus substrings with free end gaps. Host code: the data is a few
-// KB per pair and strictly sequential.
+// letterIdx (src/scoring-matrix.cpp:26-79) on the host: only used to build the 256-entry protein lookup table the kernels read
 int letterIndexHost(char type, char c) {
     if (c >= 'a' && c <= 'z') c = static_cast<char>(c - 32);
     if (type == 'p') {
@@ -159,55 +158,6 @@ int letterIndexHost(char type, char c) {
     }
 }
 
-void consensusGlobal(char type, const std::vector<float> &score, int M, float gapOpen, float gapExtend, const char *s1, int m,
-                     const char *s2, int n, std::vector<int8_t> &out) {
-    const size_t W = static_cast<size_t>(n) + 1;
-    std::vector<float> Mm((m + 1) * W, 0.0f), X((m + 1) * W, 0.0f), Y((m + 1) * W, 0.0f);
-    std::vector<int8_t> tb((m + 1) * W, 0);
-    for (int i = 1; i <= m; ++i) { Y[i * W] = -1e9; tb[i * W] = 2; }
-    for (int j = 1; j <= n; ++j) { X[j] = -1e9; tb[j] = 1; }
-    for (int i = 1; i <= m; ++i)
-        for (int j = 1; j <= n; ++j) {
-            const float base = score[letterIndexHost(type, s1[i - 1]) * M + letterIndexHost(type, s2[j - 1])];
-            const size_t c = i * W + j, up = (i - 1) * W + j, left = i * W + j - 1, dg = (i - 1) * W + j - 1;
-            Mm[c] = base + std::max({Mm[dg], X[dg], Y[dg]});
-            X[c] = std::max(Mm[up] + gapOpen, X[up] + gapExtend);
-            Y[c] = std::max(Mm[left] + gapOpen, Y[left] + gapExtend);
-            const float best = std::max({Mm[c], X[c], Y[c]});
-            tb[c] = (best == Mm[c]) ? 0 : ((best == Y[c]) ? 1 : 2);
-        }
-    std::vector<int8_t> rev;
-    int i = m, j = n;
-    while (i > 0 || j > 0) {
-        const int8_t d = tb[i * W + j];
-        rev.push_back(d);
-        if (d == 0) { --i; --j; } else if (d == 1) { --j; } else { --i; }
-    }
-    out.insert(out.end(), rev.rbegin(), rev.rend());
-}
-
-void restoreGappyColumns(char type, const std::vector<float> &score, int M, float gapOpen, float gapExtend, const int8_t *aln, int alnLen,
-                         const int32_t *runsR, int nR, const int32_t *runsQ, int nQ, const char *consR, const char *consQ,
-                         std::vector<int8_t> &out) {
-    int r = 0, q = 0, gr = 0, gq = 0;
-    for (int a = 0; a <= alnLen; ++a) {
-        const bool hitR = gr < nR && r == runsR[2 * gr];
-        const bool hitQ = gq < nQ && q == runsQ[2 * gq];
-        if (hitR && hitQ) {
-            const int lr = runsR[2 * gr + 1], lq = runsQ[2 * gq + 1];
-            consensusGlobal(type, score, M, gapOpen, gapExtend, consR + r, lr, consQ + q, lq, out);
-            ++gr; ++gq; r += lr; q += lq;
-        } else {
-            if (hitR) { out.insert(out.end(), runsR[2 * gr + 1], 2); r += runsR[2 * gr + 1]; ++gr; }
-            if (hitQ) { out.insert(out.end(), runsQ[2 * gq + 1], 1); q += runsQ[2 * gq + 1]; ++gq; }
-        }
-        if (a < alnLen) {
-            out.push_back(aln[a]);
-            if (aln[a] == 0) { ++r; ++q; } else if (aln[a] == 1) { ++q; } else if (aln[a] == 2) { ++r; }
-        }
-    }
-}
-
 size_t sideWordsL(int len, int P) { return (P == 6) ? static_cast<size_t>((len + 3) / 4) * 32 : static_cast<size_t>(len) * (P + 2); }
 
 } // namespace
@@ -219,8 +169,8 @@ void twlLevelDestroy(twl_ctx *ctx) {
     L->dSides.release(); L->dRowIn.release(); L->dRowOut.release(); L->dRowW.release(); L->dRaw.release(); L->dFreq.release();
     L->dMerged.release(); L->dCons.release(); L->dRuns.release(); L->dChunkCounts.release(); L->dUps.release();
     L->dFinalPaths.release(); L->dAaLut.release(); L->dCopies.release(); L->dStage.release(); L->hStage.release();
-    L->hRes.release(); L->hUps.release(); L->hNeedHost.release(); L->hFinal.release(); L->hSides.release(); L->hFreqPin.release(); L->hMergedPin.release();
-    L->dUps2.release(); L->dUpdPair.release(); L->dNeedHost.release(); L->dUpdIn.release();
+    L->hRes.release(); L->hUps.release(); L->hNeed.release(); L->hFinal.release(); L->hSides.release(); L->hFreqPin.release(); L->hMergedPin.release();
+    L->dUps2.release(); L->dUpdPair.release(); L->dNeed.release(); L->dWhich.release(); L->dLargeScratch.release(); L->dUpdIn.release();
     for (auto &e : L->ev) if (e) cudaEventDestroy(e);
     for (auto &e : L->sliceEv) cudaEventDestroy(e);
     if (L->stageFree) cudaEventDestroy(L->stageFree);
@@ -436,7 +386,6 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
     Trace tr;
     const int n = end - begin;
     const int nSides = 2 * n;
-    const char type = (P == 6) ? 'n' : 'p';
     const int defXdrop = static_cast<int>(1000 * -1 * ctx->gapExtend);
     std::vector<DevSide> sides(nSides);
     std::vector<const char *> rowIn;
@@ -605,7 +554,7 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
     const int nu = static_cast<int>(ups.size());
     TWL_CUDA(ctx, L->hRes.reserve(n));
     TWL_CUDA(ctx, L->hUps.reserve(std::max(nu, 1)));
-    TWL_CUDA(ctx, L->hNeedHost.reserve(std::max(nu, 1)));
+    TWL_CUDA(ctx, L->hNeed.reserve(2 * static_cast<size_t>(std::max(nu, 1))));
     TWL_CUDA(ctx, L->hFinal.reserve(std::max<size_t>(finalBytes, 16)));
     TWL_CUDA(ctx, L->hSides.reserve(nSides));
     TWL_CUDA(ctx, L->hFreqPin.reserve(std::max<size_t>(freqWords, 1)));
@@ -613,7 +562,7 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
     if (nu) {
         TWL_CUDA(ctx, L->dUps.reserve(nu));
         TWL_CUDA(ctx, L->dUpdPair.reserve(nu));
-        TWL_CUDA(ctx, L->dNeedHost.reserve(nu));
+        TWL_CUDA(ctx, L->dNeed.reserve(2 * static_cast<size_t>(nu)));
         TWL_CUDA(ctx, L->dFinalPaths.reserve(std::max<size_t>(finalBytes, 16)));
         TWL_CUDA(ctx, L->dChunkCounts.reserve(std::max<size_t>(chunkInts, 2)));
         TWL_CUDA(ctx, L->dUpdIn.reserve(std::max<size_t>(updIn.size(), 1)));
@@ -690,10 +639,9 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
         return TWL_OK;
     };
     if (nu) {
-        gappyRestoreKernel<<<std::min(nu, ctx->smCount * 32), 32, 0, ctx->stream>>>(L->dUps.ptr, L->dUpdPair.ptr, nu, ctx->dPairs.ptr, ctx->dResults.ptr,
-                                                                                   L->dSides.ptr, L->dRuns.ptr, L->dCons.ptr, ctx->dPaths.ptr,
-                                                                                   L->dFinalPaths.ptr, ctx->dScore.ptr, ctx->M, P == 6 ? 0 : 1,
-                                                                                   L->dAaLut.ptr, ctx->gapOpen, ctx->gapExtend, L->dNeedHost.ptr);
+        gappyRestoreKernel<false><<<std::min(nu, ctx->smCount * 32), 32, 0, ctx->stream>>>(
+            L->dUps.ptr, L->dUpdPair.ptr, nullptr, nu, ctx->dPairs.ptr, ctx->dResults.ptr, L->dSides.ptr, L->dRuns.ptr, L->dCons.ptr, ctx->dPaths.ptr,
+            L->dFinalPaths.ptr, ctx->dScore.ptr, ctx->M, P == 6 ? 0 : 1, L->dAaLut.ptr, ctx->gapOpen, ctx->gapExtend, L->dNeed.ptr, nullptr, 0, 0);
         TWL_CUDA(ctx, cudaGetLastError());
         ctx->lastLaunches += 1;
         const int rc = launchUpdate(L->dUps.ptr, nu, maxUb, maxRows);
@@ -707,7 +655,7 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
     TWL_CUDA(ctx, cudaMemcpyAsync(hs, L->dSides.ptr, sizeof(DevSide) * nSides, cudaMemcpyDeviceToHost, ctx->stream));
     if (nu) {
         TWL_CUDA(ctx, cudaMemcpyAsync(L->hUps.ptr, L->dUps.ptr, sizeof(DevUpdate) * nu, cudaMemcpyDeviceToHost, ctx->stream));
-        TWL_CUDA(ctx, cudaMemcpyAsync(L->hNeedHost.ptr, L->dNeedHost.ptr, sizeof(int) * nu, cudaMemcpyDeviceToHost, ctx->stream));
+        TWL_CUDA(ctx, cudaMemcpyAsync(L->hNeed.ptr, L->dNeed.ptr, sizeof(long long) * 2 * nu, cudaMemcpyDeviceToHost, ctx->stream));
         if (paths) TWL_CUDA(ctx, cudaMemcpyAsync(L->hFinal.ptr, L->dFinalPaths.ptr, finalBytes, cudaMemcpyDeviceToHost, ctx->stream));
     }
     float *hFreq = L->hFreqPin.ptr, *hMerged = L->hMergedPin.ptr;
@@ -716,40 +664,51 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
     TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     tr.mark("kernels + D2H results");
 
-    // ---- pairs whose consensus alignment did not fit the kernel's shared memory: restore on the host, update again
+    // ---- pairs with a coinciding run pair too large for the kernel's shared memory: the same kernel again with its matrices in
+    // a global scratch buffer sized from what the first pass asked for, then the row update of those pairs
     std::vector<int> redo;
-    for (int k = 0; k < nu; ++k) if (L->hNeedHost.ptr[k]) redo.push_back(k);
+    long long wantCells = kRestoreTbCells, wantCols = kRestoreRowCap;
+    for (int k = 0; k < nu; ++k)
+        if (L->hNeed.ptr[2 * k] > 0) {
+            redo.push_back(k);
+            wantCells = std::max(wantCells, L->hNeed.ptr[2 * k]);
+            wantCols = std::max(wantCols, L->hNeed.ptr[2 * k + 1]);
+        }
     if (!redo.empty()) {
+        const int nr = static_cast<int>(redo.size());
+        wantCells = (wantCells + 15) & ~15ll;
+        wantCols = (wantCols + 15) & ~15ll;
+        const size_t stride = static_cast<size_t>(wantCells) + 25ull * static_cast<size_t>(wantCols) + 64;
+        const int blocks = static_cast<int>(std::max<size_t>(1, std::min<size_t>(nr, (static_cast<size_t>(1) << 30) / stride)));
+        TWL_CUDA(ctx, L->dLargeScratch.reserve(stride * blocks));
+        TWL_CUDA(ctx, L->dWhich.reserve(nr));
+        TWL_CUDA(ctx, cudaMemcpyAsync(L->dWhich.ptr, redo.data(), sizeof(int) * nr, cudaMemcpyHostToDevice, ctx->stream));
+        gappyRestoreKernel<true><<<blocks, 32, 0, ctx->stream>>>(
+            L->dUps.ptr, L->dUpdPair.ptr, L->dWhich.ptr, nr, ctx->dPairs.ptr, ctx->dResults.ptr, L->dSides.ptr, L->dRuns.ptr, L->dCons.ptr, ctx->dPaths.ptr,
+            L->dFinalPaths.ptr, ctx->dScore.ptr, ctx->M, P == 6 ? 0 : 1, L->dAaLut.ptr, ctx->gapOpen, ctx->gapExtend, L->dNeed.ptr, L->dLargeScratch.ptr,
+            wantCells, static_cast<int>(wantCols));
+        TWL_CUDA(ctx, cudaGetLastError());
+        ctx->lastLaunches += 1;
+        TWL_CUDA(ctx, cudaMemcpyAsync(L->hUps.ptr, L->dUps.ptr, sizeof(DevUpdate) * nu, cudaMemcpyDeviceToHost, ctx->stream));
+        TWL_CUDA(ctx, cudaMemcpyAsync(L->hNeed.ptr, L->dNeed.ptr, sizeof(long long) * 2 * nu, cudaMemcpyDeviceToHost, ctx->stream));
+        TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         std::vector<DevUpdate> again;
         int maxPath = 0, rowsMax = 1;
         for (int k : redo) {
-            const int p = updPair[k];
-            const DevSide &sr = hs[2 * p], &sq = hs[2 * p + 1];
-            std::vector<int8_t> wo(std::max(res[p].pathLen, 1)), fp;
-            std::vector<int32_t> rr(2 * std::max(sr.nRuns, 1)), rq(2 * std::max(sq.nRuns, 1));
-            std::vector<char> cr(std::max(sr.alnLen, 1)), cq(std::max(sq.alnLen, 1));
-            TWL_CUDA(ctx, cudaMemcpy(wo.data(), ctx->dPaths.ptr + dp[p].alnOff, res[p].pathLen, cudaMemcpyDeviceToHost));
-            TWL_CUDA(ctx, cudaMemcpy(rr.data(), L->dRuns.ptr + sr.runsOff, sizeof(int32_t) * 2 * sr.nRuns, cudaMemcpyDeviceToHost));
-            TWL_CUDA(ctx, cudaMemcpy(rq.data(), L->dRuns.ptr + sq.runsOff, sizeof(int32_t) * 2 * sq.nRuns, cudaMemcpyDeviceToHost));
-            TWL_CUDA(ctx, cudaMemcpy(cr.data(), L->dCons.ptr + sr.consOff, sr.alnLen, cudaMemcpyDeviceToHost));
-            TWL_CUDA(ctx, cudaMemcpy(cq.data(), L->dCons.ptr + sq.consOff, sq.alnLen, cudaMemcpyDeviceToHost));
-            restoreGappyColumns(type, ctx->hScore, ctx->M, ctx->gapOpen, ctx->gapExtend, wo.data(), res[p].pathLen, rr.data(), sr.nRuns, rq.data(), sq.nRuns,
-                                cr.data(), cq.data(), fp);
-            DevUpdate &u = L->hUps.ptr[k];
-            u.pathLen = static_cast<int>(fp.size());
-            TWL_CUDA(ctx, cudaMemcpy(L->dFinalPaths.ptr + u.pathOff, fp.data(), fp.size(), cudaMemcpyHostToDevice));
-            if (paths) std::memcpy(L->hFinal.ptr + u.pathOff, fp.data(), fp.size());
+            if (L->hNeed.ptr[2 * k] > 0) return twlFail(ctx, TWL_E_STATE, "twl_align_level: gappy-column restore did not fit its scratch");
+            const DevUpdate &u = L->hUps.ptr[k];
             again.push_back(u);
             maxPath = std::max(maxPath, u.pathLen);
             rowsMax = std::max(rowsMax, u.nRef + u.nQry);
         }
         TWL_CUDA(ctx, L->dUps2.reserve(again.size()));
         TWL_CUDA(ctx, cudaMemcpyAsync(L->dUps2.ptr, again.data(), sizeof(DevUpdate) * again.size(), cudaMemcpyHostToDevice, ctx->stream));
-        const int rc = launchUpdate(L->dUps2.ptr, static_cast<int>(again.size()), maxPath, rowsMax);
+        const int rc = launchUpdate(L->dUps2.ptr, nr, maxPath, rowsMax);
         if (rc != TWL_OK) return rc;
+        if (paths) TWL_CUDA(ctx, cudaMemcpyAsync(L->hFinal.ptr, L->dFinalPaths.ptr, finalBytes, cudaMemcpyDeviceToHost, ctx->stream));
         if (mergedWords) TWL_CUDA(ctx, cudaMemcpyAsync(hMerged, L->dMerged.ptr, sizeof(float) * mergedWords, cudaMemcpyDeviceToHost, ctx->stream));
         TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        L->hostRestores += static_cast<int>(redo.size());
+        L->largeRestores += nr;
     }
 
     // ---- per pair: results, final path, row bookkeeping
@@ -857,7 +816,7 @@ int twl_align_level(twl_ctx *ctx, const twl_level_pair *pairs, int n_pairs, int 
     return TWL_OK;
 }
 
-int twl_level_host_restores(const twl_ctx *ctx) { return (ctx && ctx->level) ? ctx->level->hostRestores : 0; }
+int twl_level_large_restores(const twl_ctx *ctx) { return (ctx && ctx->level) ? ctx->level->largeRestores : 0; }
 
 int twl_level_fetch(twl_ctx *ctx, int pair, int what, void *dst, size_t cap_bytes, size_t *out_bytes) {
     if (!ctx || !ctx->level) return TWL_E_ARG;
