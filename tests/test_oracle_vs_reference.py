@@ -152,3 +152,37 @@ def test_port_coinciding_gappy_runs_equal_reference(ins_len):
     assert np.array_equal(rec.aln_wo, want["aln_wo"])
     assert np.array_equal(rec.aln_w, want["aln_w"])
     assert rec.merged.rows == want["new_rows"]
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", list(range(8)))
+def test_port_pipeline_fuzz_equals_reference(seed):
+    """Random small trees with random marker / gappy threshold / indel rate: every stage of every merge, port against the
+    unmodified reference helpers (the same generator the GPU fuzz test uses, so the oracle the GPU is checked against is
+    itself pinned on those inputs)."""
+    import copy
+    from twilight_b200 import synth
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(5, 14))
+    L = int(rng.integers(60, 500))
+    marker = int(rng.choice([32, 64, 128, 1024]))
+    gappy = float(rng.choice([0.3, 0.5, 0.7, 0.9, 0.95]))
+    _cache = int(rng.choice([2, 4, 1000]))
+    tree = synth.random_tree(n, seed=seed, mean_blen=float(rng.uniform(0.03, 0.15)))
+    seqs = synth.evolve(tree, L, seed=seed, indel_rate=float(rng.uniform(0.02, 0.25)))
+    w = rng.uniform(0.5, 1.5, n).astype(np.float32)
+    cfg = ol.TalcoCfg(marker=marker)
+    state = {i: ref_msa.leaf_state(seqs[i], w[i]) for i in range(n)}
+    for level in synth.levels_bottom_up(tree):
+        for a, b, parent in level:
+            ra, rb = state.pop(a), state.pop(b)
+            want = ol.ref_pipeline("n", cfg, copy.deepcopy(ra), copy.deepcopy(rb), gappy)
+            rec = ref_msa.align_pair("n", cfg, ra, rb, gappy)
+            assert rec.error == want["error"] == 0
+            for s in (0, 1):
+                assert np.array_equal(rec.profile[s], want["profile"][s])
+                assert np.array_equal(np.asarray(rec.runs[s]).reshape(-1, 2), want["runs"][s])
+            assert np.array_equal(rec.aln_wo, want["aln_wo"])
+            assert np.array_equal(rec.aln_w, want["aln_w"])
+            assert rec.merged.rows == want["new_rows"]
+            state[parent] = rec.merged
