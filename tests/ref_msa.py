@@ -155,3 +155,25 @@ def progressive(tree, seqs, weights, type_="n", cfg=None, gappy=0.95, talco=None
             if keep_records:
                 records.append(rec)
     return state[tree.root], records
+
+
+def talco_retry_ladder(log=None):
+    """Talco_xdrop::Align_freq inside the retry loop the reference runs for currentTask 1 and 2 (alignment-cpu.cpp:95-130):
+    errorType 2 -> fLen = min(int(fLen * 1.2) << 1, min(lens)); errorType 1 -> xdrop *= 2, fLen = min(int(xdrop * 4) << 1,
+    min(lens)); until the pair aligns (or errorType 3). `log` (a list) receives the errorType of every attempt."""
+    def fn(cfg, fr, fq, gor, ger, goq, geq, ref_num, qry_num):
+        xdrop, flen = cfg.xdrop, cfg.flen
+        min_len = min(len(fr), len(fq))
+        while True:
+            use = ol.TalcoCfg(cfg.score, cfg.gap_open, cfg.gap_extend, cfg.gap_boundary, cfg.gap_char, xdrop, flen, cfg.marker)
+            res = ol.port_talco(use, fr, fq, gor, ger, goq, geq, ref_num, qry_num)
+            if log is not None:
+                log.append(res[1])
+            if res[1] in (0, 3):
+                return res
+            if res[1] == 2:
+                flen = min(int(flen * 1.2) << 1, min_len)
+            else:
+                xdrop = xdrop * 2
+                flen = min(int(xdrop * 4) << 1, min_len)
+    return fn

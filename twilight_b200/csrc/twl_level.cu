@@ -4,6 +4,7 @@
 #include "twl_ctx.hpp"
 
 #include <algorithm>
+#include <map>
 #include <cstring>
 #include <chrono>
 #include <cstdio>
@@ -33,9 +34,12 @@ struct PairKeep {   // what twl_level_fetch needs from the last level
 
 struct TwlLevelState {
     std::vector<RowSlot> rows;
-    std::vector<void *> pools;
+    std::vector<void *> pools;            // 256 MB chunks (or one oversized request each); kept across twl_rows_clear
+    std::vector<size_t> poolBytes;
+    size_t poolNext = 0;                  // first chunk the arena has not handed out yet
     char *poolCur = nullptr;
     size_t poolLeft = 0;
+    std::map<size_t, std::vector<char *>> freeBufs;   // buffers given up by rows that outgrew them (memCheck), by size class
 
     DevBuf<twl::DevSide> dSides;
     DevBuf<const char *> dRowIn;
@@ -122,14 +126,37 @@ std::vector<int> sliceRows(const std::vector<twl::RowCopy> &list, int n) {
     return cuts;
 }
 
+// Row buffers come in size classes (3 mantissa bits: at most 12.5 % slack) so that a buffer a row has outgrown can serve
+// another row later instead of being abandoned in the arena.
+size_t rowSizeClass(size_t bytes) {
+    bytes = std::max<size_t>((bytes + 15) & ~static_cast<size_t>(15), 64);
+    int top = 63 - __builtin_clzll(bytes);
+    const size_t step = static_cast<size_t>(1) << std::max(top - 3, 4);
+    return (bytes + step - 1) & ~(step - 1);
+}
+
 cudaError_t poolAlloc(TwlLevelState *L, size_t bytes, char **out) {
-    bytes = (bytes + 15) & ~static_cast<size_t>(15);
-    if (bytes > L->poolLeft) {
+    bytes = rowSizeClass(bytes);
+    auto it = L->freeBufs.find(bytes);
+    if (it != L->freeBufs.end() && !it->second.empty()) {
+        *out = it->second.back();
+        it->second.pop_back();
+        return cudaSuccess;
+    }
+    while (bytes > L->poolLeft) {
+        if (L->poolNext < L->pools.size()) {           // a chunk kept from before twl_rows_clear
+            L->poolCur = static_cast<char *>(L->pools[L->poolNext]);
+            L->poolLeft = L->poolBytes[L->poolNext];
+            ++L->poolNext;
+            continue;
+        }
         const size_t sz = std::max(kPoolChunkBytes, bytes);
         void *p = nullptr;
         cudaError_t e = cudaMalloc(&p, sz);
         if (e != cudaSuccess) return e;
         L->pools.push_back(p);
+        L->poolBytes.push_back(sz);
+        L->poolNext = L->pools.size();
         L->poolCur = static_cast<char *>(p);
         L->poolLeft = sz;
     }
@@ -137,6 +164,10 @@ cudaError_t poolAlloc(TwlLevelState *L, size_t bytes, char **out) {
     L->poolCur += bytes;
     L->poolLeft -= bytes;
     return cudaSuccess;
+}
+
+void poolRecycle(TwlLevelState *L, char *buf, size_t cap) {
+    if (buf) L->freeBufs[rowSizeClass(cap)].push_back(buf);
 }
 
 // letterIdx (src/scoring-matrix.cpp:26-79) on the host: only used to build the 256-entry protein lookup table the kernels read
@@ -185,10 +216,12 @@ int twl_rows_clear(twl_ctx *ctx) {
     TwlLevelState *L = levelOf(ctx);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (void *p : L->pools) cudaFree(p);
-    L->pools.clear();
+    // the chunks stay allocated and are handed out again from the start (a divide-and-conquer run clears once per subtree);
+    // twl_destroy frees them. TWL_E_NOMEM recovery (host adapter) relies on the row store being empty afterwards.
+    L->poolNext = 0;
     L->poolCur = nullptr;
     L->poolLeft = 0;
+    L->freeBufs.clear();
     L->rows.clear();
     return TWL_OK;
 }
@@ -208,6 +241,7 @@ int twl_rows_upload(twl_ctx *ctx, int n, const int32_t *ids, const char *const *
         RowSlot &r = L->rows[id];
         const int cap = std::max(16, 2 * lens[i]);                        // timesBigger = 2, sequencedb.cpp:40
         if (!r.present || r.cap < lens[i]) {
+            if (r.present) { poolRecycle(L, r.buf[0], r.cap); poolRecycle(L, r.buf[1], r.cap); r.present = false; }
             TWL_CUDA(ctx, poolAlloc(L, cap, &r.buf[0]));
             TWL_CUDA(ctx, poolAlloc(L, cap, &r.buf[1]));
             r.cap = cap;
@@ -283,6 +317,7 @@ int twl_rows_import(twl_ctx *ctx, int n, const int32_t *ids, const int32_t *lens
         RowSlot &r = L->rows[id];
         const int cap = std::max(16, 2 * lens[i]);
         if (!r.present || r.cap < lens[i]) {
+            if (r.present) { poolRecycle(L, r.buf[0], r.cap); poolRecycle(L, r.buf[1], r.cap); r.present = false; }
             TWL_CUDA(ctx, poolAlloc(L, cap, &r.buf[0]));
             TWL_CUDA(ctx, poolAlloc(L, cap, &r.buf[1]));
             r.cap = cap;
@@ -364,7 +399,9 @@ int twl_level_phase_ms(twl_ctx *ctx, float out[4]) {
 // ---------------------------------------------------------------------------------------------------------------
 namespace {
 
-struct ChunkPlan { int begin, end; };
+// What runLevelChunk changed in the row store before its kernels ran: restored when the chunk fails (a CUDA error, out of
+// memory), so that a caller who handles the error code still finds every row where it was.
+struct RowUndo { int id; char *buf[2]; int cap, storage, len; };
 
 // TWL_TRACE=1: wall-clock of the host-side steps of a level chunk on stderr
 struct Trace {
@@ -380,8 +417,8 @@ struct Trace {
 };
 
 template <int P>
-int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, int begin, int end, int task, float threshold,
-                  int cacheTh, int8_t *const *paths, twl_level_result *results, int chunkNo) {
+int runLevelChunkImpl(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, int begin, int end, int task, float threshold,
+                      int cacheTh, int8_t *const *paths, twl_level_result *results, int chunkNo, std::vector<RowUndo> &journal) {
     using namespace twl;
     Trace tr;
     const int n = end - begin;
@@ -522,6 +559,7 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
             const int cnt = (s == 0) ? u.nRef : u.nQry;
             for (int m = 0; m < cnt; ++m) {
                 RowSlot &r = L->rows[sd2[s]->seq_ids[m]];
+                journal.push_back({sd2[s]->seq_ids[m], {r.buf[0], r.buf[1]}, r.cap, r.storage, r.len});
                 updIn.push_back(r.buf[r.storage]);
                 if (r.cap < ub) {                                            // SequenceInfo::memCheck, sequencedb.cpp:57-76
                     const int cap = 2 * ub;
@@ -555,7 +593,6 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
     TWL_CUDA(ctx, L->hRes.reserve(n));
     TWL_CUDA(ctx, L->hUps.reserve(std::max(nu, 1)));
     TWL_CUDA(ctx, L->hNeed.reserve(2 * static_cast<size_t>(std::max(nu, 1))));
-    TWL_CUDA(ctx, L->hFinal.reserve(std::max<size_t>(finalBytes, 16)));
     TWL_CUDA(ctx, L->hSides.reserve(nSides));
     TWL_CUDA(ctx, L->hFreqPin.reserve(std::max<size_t>(freqWords, 1)));
     TWL_CUDA(ctx, L->hMergedPin.reserve(std::max<size_t>(mergedWords, 1)));
@@ -575,6 +612,10 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
             TWL_CUDA(ctx, cudaMemcpyAsync(L->dRowOut.ptr, updOut.data(), sizeof(char *) * updOut.size(), cudaMemcpyHostToDevice, ctx->stream));
         }
     }
+    // final paths travel to the host only when the caller gave a destination for at least one pair of the chunk
+    bool wantPaths = false;
+    if (paths) for (int p = 0; p < n && !wantPaths; ++p) wantPaths = paths[begin + p] != nullptr && upOfPair[p] >= 0;
+    if (wantPaths) TWL_CUDA(ctx, L->hFinal.reserve(std::max<size_t>(finalBytes, 16)));
     DevResult *res = L->hRes.ptr;
     for (int p = 0; p < n; ++p) { res[p].status = 0; res[p].pathLen = 0; res[p].tiles = 0; res[p].pad = 0; res[p].cells = 0; res[p].diagonals = 0; }
 
@@ -656,7 +697,7 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
     if (nu) {
         TWL_CUDA(ctx, cudaMemcpyAsync(L->hUps.ptr, L->dUps.ptr, sizeof(DevUpdate) * nu, cudaMemcpyDeviceToHost, ctx->stream));
         TWL_CUDA(ctx, cudaMemcpyAsync(L->hNeed.ptr, L->dNeed.ptr, sizeof(long long) * 2 * nu, cudaMemcpyDeviceToHost, ctx->stream));
-        if (paths) TWL_CUDA(ctx, cudaMemcpyAsync(L->hFinal.ptr, L->dFinalPaths.ptr, finalBytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (wantPaths) TWL_CUDA(ctx, cudaMemcpyAsync(L->hFinal.ptr, L->dFinalPaths.ptr, finalBytes, cudaMemcpyDeviceToHost, ctx->stream));
     }
     float *hFreq = L->hFreqPin.ptr, *hMerged = L->hMergedPin.ptr;
     if (freqWords) TWL_CUDA(ctx, cudaMemcpyAsync(hFreq, L->dFreq.ptr, sizeof(float) * freqWords, cudaMemcpyDeviceToHost, ctx->stream));
@@ -705,7 +746,7 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
         TWL_CUDA(ctx, cudaMemcpyAsync(L->dUps2.ptr, again.data(), sizeof(DevUpdate) * again.size(), cudaMemcpyHostToDevice, ctx->stream));
         const int rc = launchUpdate(L->dUps2.ptr, nr, maxPath, rowsMax);
         if (rc != TWL_OK) return rc;
-        if (paths) TWL_CUDA(ctx, cudaMemcpyAsync(L->hFinal.ptr, L->dFinalPaths.ptr, finalBytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (wantPaths) TWL_CUDA(ctx, cudaMemcpyAsync(L->hFinal.ptr, L->dFinalPaths.ptr, finalBytes, cudaMemcpyDeviceToHost, ctx->stream));
         if (mergedWords) TWL_CUDA(ctx, cudaMemcpyAsync(hMerged, L->dMerged.ptr, sizeof(float) * mergedWords, cudaMemcpyDeviceToHost, ctx->stream));
         TWL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         L->largeRestores += nr;
@@ -747,7 +788,7 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
             kp.merged.assign(hMerged + u.mergedOff, hMerged + u.mergedOff + static_cast<size_t>(u.pathLen) * P);
         }
     }
-    if (paths && nu)
+    if (wantPaths && nu)
         parallelRows(n, finalBytes, [&](int b, int e) {
             for (int p = b; p < e; ++p) {
                 const twl_level_result &out = results[begin + p];
@@ -756,6 +797,12 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
             }
         });
     tr.mark("results to caller (host)");
+    // buffers that regrown rows left behind serve other rows from now on (everything that read them is stream-ordered before)
+    for (const RowUndo &u : journal) {
+        const RowSlot &r = L->rows[u.id];
+        if (r.buf[0] != u.buf[0]) { poolRecycle(L, u.buf[0], u.cap); poolRecycle(L, u.buf[1], u.cap); }
+    }
+    journal.clear();
     const bool updateTimed = nu > 0;
     for (int i = 0; i < 3; ++i) {
         float ms = 0.f;
@@ -768,6 +815,24 @@ int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, i
         L->phaseMs[3] += ms;
     }
     return TWL_OK;
+}
+
+template <int P>
+int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, int begin, int end, int task, float threshold,
+                  int cacheTh, int8_t *const *paths, twl_level_result *results, int chunkNo) {
+    std::vector<RowUndo> journal;
+    const int rc = runLevelChunkImpl<P>(ctx, L, pairs, begin, end, task, threshold, cacheTh, paths, results, chunkNo, journal);
+    if (rc != TWL_OK) {
+        // nothing of this chunk counts: rows point at their old buffers again (whatever was enqueued only wrote the other
+        // buffer of each row, or buffers that were freshly allocated and are dropped here)
+        cudaStreamSynchronize(ctx->stream);
+        for (auto it = journal.rbegin(); it != journal.rend(); ++it) {
+            RowSlot &r = L->rows[it->id];
+            r.buf[0] = it->buf[0]; r.buf[1] = it->buf[1]; r.cap = it->cap; r.storage = it->storage; r.len = it->len;
+        }
+        cudaGetLastError();
+    }
+    return rc;
 }
 
 } // namespace

@@ -255,3 +255,73 @@ def level_rows_batch(n_pairs: int, length: int, seed: int = 0, kind: str = "rna"
         b = _mutate(root, divergence / 2, rng, alphabet, indel_rate, probs)
         out.append((family_rows(a, int(rng.choice(members)), rng, kind), family_rows(b, int(rng.choice(members)), rng, kind)))
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Whole data sets on disk (FASTA + Newick) for the drop-in CLI: the named shapes of BASELINE.json at reduced N.
+# ------------------------------------------------------------------------------------------------------------------
+def tree_depth(tree: Tree) -> int:
+    depth = np.zeros(tree.n_nodes, np.int32)
+    for v in reversed(tree.postorder()):
+        for c in tree.children[v]:
+            depth[c] = depth[v] + 1
+    return int(depth.max())
+
+
+def write_dataset(prefix: str, tree: Tree, seqs: List[bytes], width: int = 0):
+    """<prefix>.fa (one record per leaf, names L<i>) and <prefix>.nwk."""
+    with open(prefix + ".fa", "wb") as f:
+        for name, s in zip(tree.names, seqs):
+            f.write(b">" + name.encode() + b"\n")
+            if width:
+                for k in range(0, len(s), width):
+                    f.write(s[k:k + width] + b"\n")
+            else:
+                f.write(s + b"\n")
+    with open(prefix + ".nwk", "w") as f:
+        f.write(tree.newick() + "\n")
+
+
+DATASETS = {
+    # name: (leaves, root length, kind, root-to-tip divergence, indel rate, N fraction, seed)
+    "rna_1k": (1000, 1500, "rna", 0.30, 0.03, 0.0, 11),        # C3 rung 10^3 (forces nothing special: < 1000 per node until the top)
+    "rna_3k": (3000, 1500, "rna", 0.30, 0.03, 0.0, 12),        # msaFreq caching + parking (>= 1000 sequences per node)
+    "rna_10k": (10000, 1500, "rna", 0.30, 0.03, 0.0, 13),      # C3 rung 10^4
+    "sars_64": (64, 29700, "dna", 0.002, 0.002, 0.0001, 14),   # C4 shape: 30 kb, near-identical, rare short indels
+    "prot_2k": (2000, 400, "protein", 0.45, 0.02, 0.0, 15),    # C5 shape: 400 aa, BLOSUM62
+    # 300 leaves of which 3 carry 15 % N (low quality, io.cpp:131-163: excluded, or deferred with --no-filtering), 3 are
+    # unrelated random sequences and 2 are half-length fragments (pairs that fail the x-drop rule are deferred and
+    # re-aligned with the widening ladder, alignment-cpu.cpp:108-129, progressive.cpp:275-298)
+    "rna_outliers": (300, 1500, "rna", 0.30, 0.03, 0.0, 16),
+}
+
+
+def make_dataset(name: str, out_dir: str) -> str:
+    """Writes the named synthetic data set and returns the path prefix (.fa / .nwk)."""
+    import os
+    n, length, kind, div, indel, nfrac, seed = DATASETS[name]
+    tree = random_tree(n, seed=seed, mean_blen=1.0)
+    # scale branch lengths so that the mean root-to-tip distance is `div`
+    dist = np.zeros(tree.n_nodes, np.float64)
+    for v in reversed(tree.postorder()):
+        for c in tree.children[v]:
+            dist[c] = dist[v] + float(tree.blen[c])
+    scale = div / float(dist[:n].mean())
+    tree.blen = (tree.blen.astype(np.float64) * scale).astype(np.float32)
+    seqs = evolve(tree, length, seed=seed, kind=kind, indel_rate=indel, n_frac=nfrac)
+    if name == "rna_outliers":
+        rng = np.random.default_rng(seed + 1)
+        pick = rng.choice(n, size=8, replace=False)
+        for k, leaf in enumerate(pick):
+            s = np.frombuffer(seqs[leaf], np.uint8).copy()
+            if k < 3:
+                s[rng.random(len(s)) < 0.15] = ord("N")
+            elif k < 6:
+                s = rng.choice(RNA, size=len(s))
+            else:
+                s = s[: len(s) // 2]
+            seqs[leaf] = s.tobytes()
+    os.makedirs(out_dir, exist_ok=True)
+    prefix = os.path.join(out_dir, name)
+    write_dataset(prefix, tree, seqs)
+    return prefix
