@@ -14,6 +14,7 @@
 #include "TALCO-XDrop.hpp"
 #include <tbb/parallel_for.h>
 
+#include <chrono>
 #include <cstring>
 #include <new>
 #include <string>
@@ -243,6 +244,55 @@ int ref_pair_pipeline(char type, int currentTask, float gappyVertical, const flo
     delete b;
     delete mp;
     return 0;
+}
+
+// One guide-tree level through the reference's own level entry point, msa::progressive::cpu::alignmentKernel_CPU ->
+// parallelAlignmentCPU (src/alignment-cpu.cpp:32-183): the stock call the scheduler makes at src/progressive.cpp:180, on a
+// real NodePairVec / SequenceDB built from flat inputs. Its tbb::parallel_for over the pairs runs on `threads` workers.
+//   nSeq/alnLen/alnNum/alnWeight  [2*nPairs]  (ref side at 2p, qry side at 2p+1); rows/weights: all member rows in that order
+// Outputs: newLen[p] = first->alnLen after the call (0 for a deferred pair); *seconds = wall time of the level call alone
+// (node / DB construction excluded). Returns the number of pairs the reference deferred (db->fallback_nodes).
+int ref_level_cpu(char type, int currentTask, float gappyVertical, const float *score, float gapOpen, float gapExtend,
+                  float gapBoundary, int nPairs, const int *nSeq, const char *const *rows, const float *weights,
+                  const int *alnLen, const int *alnNum, const float *alnWeight, int threads, int *newLen, double *seconds) {
+    using namespace msa;
+    const int P = (type == 'n') ? 6 : 22;
+    Params *mp = makeParams(type, score, gapOpen, gapExtend, gapBoundary);
+    OptionBox ob(type, gappyVertical, 0);
+    ob.get()->cpuNum = threads;
+    SequenceDB *db = new SequenceDB();
+    db->currentTask = currentTask;
+    std::vector<Node *> owned;
+    NodePairVec level;
+    int nextId = 0;
+    size_t at = 0;
+    for (int p = 0; p < nPairs; ++p) {
+        Node *nd[2];
+        for (int s = 0; s < 2; ++s) {
+            const int k = 2 * p + s;
+            nd[s] = new Node((s ? "q" : "r") + std::to_string(p), 0.f);
+            owned.push_back(nd[s]);
+            SideIn in{nSeq[k], rows + at, weights + at, alnLen[k], alnNum[k], alnWeight[k], nullptr};
+            fillNode(nd[s], db, in, P, nextId, false);
+            at += static_cast<size_t>(nSeq[k]);
+        }
+        level.push_back(std::make_pair(nd[0], nd[1]));
+    }
+    const int before = tbb::compat_detail::parallelism_cap();
+    tbb::compat_detail::parallelism_cap() = threads < 1 ? 1 : threads;
+    const auto t0 = std::chrono::steady_clock::now();
+    progressive::cpu::alignmentKernel_CPU(nullptr, level, db, ob.get(), *mp);
+    const auto t1 = std::chrono::steady_clock::now();
+    tbb::compat_detail::parallelism_cap() = before;
+    if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+    const int deferred = static_cast<int>(db->fallback_nodes.size());
+    for (int p = 0; p < nPairs; ++p)
+        if (newLen) newLen[p] = level[p].second->seqsIncluded.empty() ? level[p].first->alnLen : 0;
+    for (auto *si : db->sequences) delete si;
+    delete db;
+    for (Node *n : owned) delete n;
+    delete mp;
+    return deferred;
 }
 
 // Worker cap for the compat parallel_for (the reference does this with tbb::global_control, twilight-main.cpp:117).

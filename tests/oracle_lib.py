@@ -203,6 +203,31 @@ def ref_pipeline(type_, cfg, ref_state, qry_state, gappy=0.95, current_task=0):
     return res
 
 
+def ref_level(type_, cfg, pairs, threads, gappy=0.95, current_task=0):
+    """One guide-tree level through the reference's OWN level entry point (cpu::alignmentKernel_CPU ->
+    parallelAlignmentCPU, src/alignment-cpu.cpp:32-183; oracle/ref_shim.cpp::ref_level_cpu). `pairs` is a list of
+    (ref NodeState, qry NodeState). Returns (new alnLen per pair, seconds inside the level call, pairs deferred)."""
+    lib = ref()
+    fn = lib.ref_level_cpu
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_char, C.c_int, C.c_float, f32p, C.c_float, C.c_float, C.c_float, C.c_int, i32p, C.POINTER(C.c_char_p), f32p,
+                   i32p, i32p, f32p, C.c_int, i32p, C.POINTER(C.c_double)]
+    n = len(pairs)
+    sides = [st for pr in pairs for st in pr]
+    rows = [r for st in sides for r in st.rows]
+    arr = (C.c_char_p * max(len(rows), 1))(*rows)
+    w = np.ascontiguousarray(np.concatenate([np.asarray(st.weights, np.float32) for st in sides]) if sides else np.zeros(1, np.float32))
+    n_seq = np.array([len(st.rows) for st in sides], np.int32)
+    aln_len = np.array([st.aln_len for st in sides], np.int32)
+    aln_num = np.array([st.aln_num for st in sides], np.int32)
+    aln_w = np.array([st.aln_weight for st in sides], np.float32)
+    new_len = np.zeros(max(n, 1), np.int32)
+    sec = C.c_double(0)
+    deferred = fn(type_.encode(), current_task, gappy, cfg.score, cfg.gap_open, cfg.gap_extend, cfg.gap_boundary, n, n_seq, arr, w,
+                  aln_len, aln_num, aln_w, int(threads), new_len, C.byref(sec))
+    return new_len[:n].copy(), sec.value, deferred
+
+
 _B62_NCBI_ORDER = "ARNDCQEGHILKMFPSTWYV"
 _B62_NCBI = """
  4 -1 -2 -2  0 -1 -1  0 -2 -1 -1 -1 -1 -2 -1  1  0 -3 -2  0

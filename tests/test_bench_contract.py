@@ -26,6 +26,13 @@ def test_reference_arm_prints_one_contract_line():
     assert d["value"] > 0 and "workload" in d["config"]
     assert d["e2e"] == {"value": d["value"], "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["mcups_per_core"] > 0
+    # the config is a function of the arguments only, so the B200 arm run with the same arguments prints the same dict
+    sys.path.insert(0, ROOT)
+    import argparse
+    import bench
+    same = bench.level_config(argparse.Namespace(pairs=8, length=1500, seeds=3))
+    assert d["config"] == same
 
 
 def test_reference_arm_is_silent_on_other_ranks():

@@ -186,3 +186,20 @@ def test_port_pipeline_fuzz_equals_reference(seed):
             assert np.array_equal(rec.aln_w, want["aln_w"])
             assert rec.merged.rows == want["new_rows"]
             state[parent] = rec.merged
+
+
+def test_reference_level_entry_matches_port():
+    """The stock level call (cpu::alignmentKernel_CPU -> parallelAlignmentCPU on a real NodePairVec, oracle/ref_shim.cpp::
+    ref_level_cpu — what `bench.py --impl reference` times) yields the same merged lengths as the port's per-pair pipeline."""
+    if not ol.have_ref():
+        pytest.skip("oracle/_ref/libtalco_ref.so not built")
+    from tests import ref_msa
+    from twilight_b200 import synth
+    fam = synth.level_rows_batch(12, 500, seed=5, kind="rna")
+    cfg = ol.TalcoCfg()
+
+    def st(rows):
+        return ref_msa.NodeState(rows, np.ones(len(rows), np.float32), len(rows[0]), len(rows), float(len(rows)))
+    new_len, seconds, deferred = ol.ref_level("n", cfg, [(st(a), st(b)) for a, b in fam], threads=4)
+    want = [len(ref_msa.align_pair("n", cfg, st(a), st(b)).aln_w) for a, b in fam]
+    assert list(new_len) == want and deferred == 0 and seconds > 0

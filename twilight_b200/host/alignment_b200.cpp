@@ -25,6 +25,8 @@
 #include <tbb/spin_rw_mutex.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -48,6 +50,27 @@ struct Device {
     std::vector<float> score;
 };
 
+// TWL_STATS=1: one JSON line on stderr at exit with what the device did for this run (bench.py reads it for the
+// BASELINE.json configs that go through the CLI): device milliseconds by phase, DP cell updates, pairs, levels,
+// bytes moved each way, and the wall time spent inside the level calls (host bookkeeping included).
+struct Stats {
+    bool on = false;
+    double phaseMs[4] = {0, 0, 0, 0}, wallMs = 0;
+    unsigned long long cells = 0, pairs = 0, levels = 0, h2dBytes = 0, d2hBytes = 0, deferred = 0;
+};
+Stats &stats() {
+    static Stats s;
+    return s;
+}
+void printStats() {
+    const Stats &s = stats();
+    std::fprintf(stderr, "[twl-stats] {\"levels\": %llu, \"pairs\": %llu, \"deferred_pairs\": %llu, \"cells\": %llu, \"device_ms\": %.3f, "
+                 "\"phase_ms\": {\"profile_build\": %.3f, \"gappy_psgp_pack\": %.3f, \"dp_chain\": %.3f, \"row_update_freq_merge\": %.3f}, "
+                 "\"level_calls_wall_ms\": %.3f, \"h2d_row_bytes\": %llu, \"d2h_row_bytes\": %llu}\n",
+                 s.levels, s.pairs, s.deferred, s.cells, s.phaseMs[0] + s.phaseMs[1] + s.phaseMs[2] + s.phaseMs[3], s.phaseMs[0], s.phaseMs[1],
+                 s.phaseMs[2], s.phaseMs[3], s.wallMs, s.h2dBytes, s.d2hBytes);
+}
+
 Device &device() {
     static Device d;
     return d;
@@ -64,7 +87,11 @@ void ensureContext(Params &param) {
         const char *env = std::getenv("TWL_DEVICE");
         const int dev = env ? std::atoi(env) : 0;
         if (twl_init(dev, &d.ctx) != TWL_OK) die("cannot initialise the CUDA device", twl_last_error(nullptr));
-        std::atexit([] { if (device().ctx) { twl_destroy(device().ctx); device().ctx = nullptr; } });
+        stats().on = std::getenv("TWL_STATS") != nullptr;
+        std::atexit([] {
+            if (stats().on) printStats();
+            if (device().ctx) { twl_destroy(device().ctx); device().ctx = nullptr; }
+        });
     }
     const int M = param.matrixSize;
     std::vector<float> flat(static_cast<size_t>(M) * M);
@@ -111,6 +138,7 @@ void downloadRows(SequenceDB *database, const std::vector<int32_t> &ids) {
             bytes += static_cast<size_t>(seq->len);
             ++end;
         }
+        stats().d2hBytes += bytes;
         if (twl_rows_download(ctx, static_cast<int>(end - at), ids.data() + at, dst.data(), nullptr) != TWL_OK)
             die("twl_rows_download", twl_last_error(ctx));
         at = end;
@@ -167,6 +195,7 @@ void alignmentKernel_B200_level(Tree *tree, NodePairVec &nodes, SequenceDB *data
     ensureContext(param);
     twl_ctx *ctx = device().ctx;
     RowState &rs = rowState();
+    const auto wall0 = std::chrono::steady_clock::now();
     if (rs.db != database) beginSubtree(database);                         // called outside the msaOnSubtree wrapper
     const int P = param.matrixSize + 1;
     const int task = database->currentTask;
@@ -249,6 +278,16 @@ void alignmentKernel_B200_level(Tree *tree, NodePairVec &nodes, SequenceDB *data
             }
     }
 
+    if (stats().on) {
+        Stats &st = stats();
+        float ph[4] = {0, 0, 0, 0};
+        twl_level_phase_ms(ctx, ph);
+        for (int i = 0; i < 4; ++i) st.phaseMs[i] += ph[i];
+        st.levels += 1;
+        st.pairs += static_cast<unsigned long long>(nPairs);
+        for (int n = 0; n < nPairs; ++n) st.cells += out[n].cells;
+        for (int32_t len : upLens) st.h2dBytes += static_cast<unsigned long long>(len);
+    }
     std::vector<int> fallbackPairs;
     std::vector<int32_t> parkedIds;
     for (int n = 0; n < nPairs; ++n) {
@@ -325,8 +364,11 @@ void alignmentKernel_B200_level(Tree *tree, NodePairVec &nodes, SequenceDB *data
         }
     }
     downloadRows(database, parkedIds);
-    if (fallbackPairs.empty()) return;
-    alignment_helper::fallback2cpu(fallbackPairs, nodes, database, option);
+    if (!fallbackPairs.empty()) alignment_helper::fallback2cpu(fallbackPairs, nodes, database, option);
+    if (stats().on) {
+        stats().deferred += fallbackPairs.size();
+        stats().wallMs += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+    }
 }
 
 } // namespace b200
