@@ -318,6 +318,14 @@ def run_named_configs(flush):
         "C4", "dna", 64, 29700, 3, 2, flush, 16, dict(divergence=0.004, indel_rate=0.002, members=(1, 2, 4, 8)),
         "one guide-tree level of 64 node pairs of SARS-CoV-2-length genomes (~29.7 kb, 1-8 members per node, tip identity ~99.6 %): "
         "long pairs, ~58 TALCO tiles each")
+    try:   # the reference's own CUDA kernel on the same B200 and level shape ("the existing GPU kernel to beat")
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("ref_gpu_kernel", os.path.join(ROOT, "tools", "ref_gpu_kernel.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        out["reference_gpu_kernel_same_level"] = mod.run(4096, 1500, 1000, "rna")
+    except Exception as e:
+        out["reference_gpu_kernel_same_level"] = {"error": repr(e)}
     out["C5_level_protein"] = run_level_config(
         "C5", "protein", 4096, 400, 3, 2, flush, 16 * (os.cpu_count() or 1), dict(divergence=0.4, indel_rate=0.02, members=(1, 2, 4, 8)),
         "one guide-tree level of 4096 node pairs of ~400-aa protein families (1-8 members per node), 5 x BLOSUM62, --type p semantics")

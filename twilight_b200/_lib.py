@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libtwilight_b200.so")
+# TWL_LIB points the binding at another build of the same library (A/B timing of kernel variants, tools/dp_ab.py)
+LIB_PATH = os.environ.get("TWL_LIB") or os.path.join(PKG, "libtwilight_b200.so")
 
 TWL_OK = 0
 ERRORS = {-1: "TWL_E_NO_DEVICE", -2: "TWL_E_CUDA", -3: "TWL_E_ARG", -4: "TWL_E_NOMEM", -5: "TWL_E_STATE"}

@@ -289,7 +289,8 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
             const int threads = plan[s][0], slots = plan[s][1];
             if (useWarp && s == 0) continue;
             const int cap = twl::wavefrontBandCapacity(threads, slots);
-            const int perSm = std::max(1, twl::wavefrontMaxCtasPerSm(threads, slots, matClass));
+            int perSm = std::max(1, twl::wavefrontMaxCtasPerSm(threads, slots, matClass));
+            if (ctx->maxCtasPerSm > 0) perSm = std::min(perSm, ctx->maxCtasPerSm);
             stages.push_back({0, threads, cap, std::min(n, ctx->smCount * perSm), tbRows(twl::wavefrontWindow(threads, slots)), slots});
             if (wideCap <= cap) break;
         }
@@ -305,7 +306,8 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
     int wideGrid = 0;
     bool takeMain = false;
     if (coRun) {
-        const int perSm = std::max(1, twl::wavefrontMaxCtasPerSm(stages[0].threads, stages[0].slots, matClass));
+        int perSm = std::max(1, twl::wavefrontMaxCtasPerSm(stages[0].threads, stages[0].slots, matClass));
+        if (ctx->maxCtasPerSm > 0) perSm = std::min(perSm, ctx->maxCtasPerSm);
         // Many pairs per narrow CTA slot: a few wide workers that also eat from the main queue. About one wave or less: the
         // wide workers take the SMs the narrow kernel does not need and only serve handed-over pairs, which then restart at once.
         takeMain = n > ctx->smCount * perSm;
@@ -514,6 +516,7 @@ int twl_set_option(twl_ctx *ctx, const char *name, int value) {
     if (std::strcmp(name, "wide_threads") == 0) { if (value != 256 && value != 512) return TWL_E_ARG; ctx->wideThreads = value; return TWL_OK; }
     if (std::strcmp(name, "wide_workers") == 0) { ctx->wideWorkers = std::max(0, value); return TWL_OK; }
     if (std::strcmp(name, "dp_trace") == 0) { ctx->dpTrace = value; return TWL_OK; }
+    if (std::strcmp(name, "max_ctas_per_sm") == 0) { ctx->maxCtasPerSm = std::max(0, value); return TWL_OK; }   // occupancy experiments (0 = what fits)
     if (std::strcmp(name, "latency_shape") == 0) { ctx->latencyShape = value; return TWL_OK; }   // 0: 256x2, 1: 512x1
     if (std::strcmp(name, "latency_mode") == 0) { ctx->latencyMode = value; return TWL_OK; }     // -1 auto, 0 off, 1 always
     if (std::strcmp(name, "dp_kernel") == 0) { ctx->dpKernel = value; return TWL_OK; }             // 0 auto, 1 CTA per pair, 2 warp per pair

@@ -81,6 +81,7 @@ struct twl_ctx {
     int dpKernel = 1;            // nucleotide first stage: 0 auto, 1 CTA per pair (talco_wavefront.cu), 2 warp per pair (talco_warp.cu)
     int latencyMode = -1;        // 256x2 low-latency wavefront variant for levels with <= smCount pairs: -1 auto, 0 off, 1 always
     int dpTrace = 0;
+    int maxCtasPerSm = 0;        // cap on resident CTAs per SM of the wavefront stages (0 = as many as fit); occupancy experiments
     int wideWorkers = 8;         // CTAs of the wide wavefront kernel that run next to the narrow one (0 = run the wide stage afterwards)
     cudaStream_t stream2 = nullptr;
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
