@@ -106,6 +106,12 @@ int twl_rows_download(twl_ctx *ctx, int n, const int32_t *ids, char *const *dst,
 int twl_rows_export(twl_ctx *ctx, int n, const int32_t *ids, void *dev_dst, size_t cap_bytes, int32_t *lens, int64_t *offsets);
 int twl_rows_import(twl_ctx *ctx, int n, const int32_t *ids, const int32_t *lens, const float *weights, const void *dev_src,
                     const int64_t *offsets);
+/* Multi-GPU inside ONE process (one context per device, as the reference's per-GPU GPU_pointers objects,
+ * src/cuda/alignment-gpu.cu:226-253): move n rows from the context that holds them to another context's device — packed on the
+ * source, one cudaMemcpyPeer over NVLink / NVSwitch (peer access is enabled on first use), unpacked on the destination; the
+ * rows are gone from `src` afterwards. twl_rows_drop forgets rows (their buffers are reused by later rows). */
+int twl_rows_migrate(twl_ctx *src, twl_ctx *dst, int n, const int32_t *ids);
+int twl_rows_drop(twl_ctx *ctx, int n, const int32_t *ids);
 int twl_rows_length(twl_ctx *ctx, int32_t id);
 /* The same for n rows at once: lens[i] = current length of row ids[i], or -1. */
 int twl_rows_lengths(twl_ctx *ctx, int n, const int32_t *ids, int32_t *lens);   /* current length of a row, <0 if unknown */

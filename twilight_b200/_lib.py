@@ -58,6 +58,8 @@ SIGNATURES = {
     "twl_rows_download": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
     "twl_rows_export": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_void_p, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "twl_rows_import": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float), C.c_void_p, C.POINTER(C.c_int64)]),
+    "twl_rows_migrate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int32)]),
+    "twl_rows_drop": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32)]),
     "twl_rows_length": (C.c_int, [C.c_void_p, C.c_int32]),
     "twl_rows_lengths": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "twl_rows_clear": (C.c_int, [C.c_void_p]),

@@ -325,6 +325,15 @@ class Context:
     def align_level_prepared(self, prep, task: int = 0, gappy: float = 0.95, cache_threshold: int = 1000):
         self._check(self._lib.twl_align_level(self._h, prep.arr, prep.n, int(task), float(gappy), int(cache_threshold), prep.ptrs, prep.res))
 
+    def rows_migrate_to(self, other: "Context", ids: Sequence[int]):
+        """Moves rows to another context's device (twl_rows_migrate: pack, cudaMemcpyPeer over NVLink, unpack); they leave this one."""
+        arr = (C.c_int32 * max(len(ids), 1))(*[int(i) for i in ids])
+        self._check(self._lib.twl_rows_migrate(self._h, other._h, len(ids), arr))
+
+    def rows_drop(self, ids: Sequence[int]):
+        arr = (C.c_int32 * max(len(ids), 1))(*[int(i) for i in ids])
+        self._check(self._lib.twl_rows_drop(self._h, len(ids), arr))
+
     def rows_clear(self):
         self._check(self._lib.twl_rows_clear(self._h))
 

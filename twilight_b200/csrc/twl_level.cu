@@ -334,6 +334,84 @@ int twl_rows_import(twl_ctx *ctx, int n, const int32_t *ids, const int32_t *lens
     return TWL_OK;
 }
 
+int twl_rows_drop(twl_ctx *ctx, int n, const int32_t *ids) {
+    if (!ctx) return TWL_E_ARG;
+    if (n < 0 || (n > 0 && !ids)) return twlFail(ctx, TWL_E_ARG, "twl_rows_drop: null argument");
+    TwlLevelState *L = levelOf(ctx);
+    for (int i = 0; i < n; ++i) {
+        if (ids[i] < 0 || static_cast<size_t>(ids[i]) >= L->rows.size() || !L->rows[ids[i]].present) continue;
+        RowSlot &r = L->rows[ids[i]];
+        poolRecycle(L, r.buf[0], r.cap);       // everything that still reads the buffers is stream-ordered before their next use
+        poolRecycle(L, r.buf[1], r.cap);
+        r = RowSlot();
+    }
+    return TWL_OK;
+}
+
+int twl_rows_migrate(twl_ctx *src, twl_ctx *dst, int n, const int32_t *ids) {
+    if (!src || !dst) return TWL_E_ARG;
+    if (n < 0 || (n > 0 && !ids)) return twlFail(src, TWL_E_ARG, "twl_rows_migrate: null argument");
+    if (n == 0 || src == dst) return TWL_OK;
+    TwlLevelState *LS = levelOf(src), *LD = levelOf(dst);
+    // pack on the source device
+    std::vector<twl::RowCopy> list(n);
+    std::vector<int32_t> lens(n);
+    std::vector<float> weights(n);
+    size_t total = 0;
+    for (int i = 0; i < n; ++i) {
+        if (ids[i] < 0 || static_cast<size_t>(ids[i]) >= LS->rows.size() || !LS->rows[ids[i]].present)
+            return twlFail(src, TWL_E_ARG, "twl_rows_migrate: unknown row id " + std::to_string(ids[i]));
+        const RowSlot &r = LS->rows[ids[i]];
+        list[i].dev = r.buf[r.storage]; list[i].stageOff = static_cast<long long>(total); list[i].len = r.len; list[i].pad = 0;
+        lens[i] = r.len; weights[i] = r.weight;
+        total += (static_cast<size_t>(r.len) + 15) & ~static_cast<size_t>(15);
+    }
+    cudaSetDevice(src->device);
+    if (LS->stagePending) { TWL_CUDA(src, cudaEventSynchronize(LS->stageFree)); LS->stagePending = false; }
+    TWL_CUDA(src, LS->dStage.reserve(std::max<size_t>(total, 16)));
+    TWL_CUDA(src, LS->dCopies.reserve(n));
+    TWL_CUDA(src, cudaMemcpyAsync(LS->dCopies.ptr, list.data(), sizeof(twl::RowCopy) * n, cudaMemcpyHostToDevice, src->stream));
+    twl::rowTransferKernel<<<(n * 32 + 255) / 256, 256, 0, src->stream>>>(LS->dCopies.ptr, n, LS->dStage.ptr, 0);
+    TWL_CUDA(src, cudaGetLastError());
+    TWL_CUDA(src, cudaStreamSynchronize(src->stream));
+    // device to device (NVLink / NVSwitch when peer access is possible; the runtime stages through the host otherwise)
+    cudaSetDevice(dst->device);
+    if (LD->stagePending) { TWL_CUDA(dst, cudaEventSynchronize(LD->stageFree)); LD->stagePending = false; }
+    TWL_CUDA(dst, LD->dStage.reserve(std::max<size_t>(total, 16)));
+    if (src->device != dst->device) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, dst->device, src->device) == cudaSuccess && can) {
+            const cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return twlFail(dst, TWL_E_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+        TWL_CUDA(dst, cudaMemcpyPeerAsync(LD->dStage.ptr, dst->device, LS->dStage.ptr, src->device, total, dst->stream));
+    } else {
+        TWL_CUDA(dst, cudaMemcpyAsync(LD->dStage.ptr, LS->dStage.ptr, total, cudaMemcpyDeviceToDevice, dst->stream));
+    }
+    // unpack on the destination device
+    for (int i = 0; i < n; ++i) {
+        const int id = ids[i];
+        if (static_cast<size_t>(id) >= LD->rows.size()) LD->rows.resize(id + 1);
+        RowSlot &r = LD->rows[id];
+        const int cap = std::max(16, 2 * lens[i]);
+        if (!r.present || r.cap < lens[i]) {
+            if (r.present) { poolRecycle(LD, r.buf[0], r.cap); poolRecycle(LD, r.buf[1], r.cap); r.present = false; }
+            TWL_CUDA(dst, poolAlloc(LD, cap, &r.buf[0]));
+            TWL_CUDA(dst, poolAlloc(LD, cap, &r.buf[1]));
+            r.cap = cap;
+        }
+        r.len = lens[i]; r.storage = 0; r.weight = weights[i]; r.present = true;
+        list[i].dev = r.buf[0];
+    }
+    TWL_CUDA(dst, LD->dCopies.reserve(n));
+    TWL_CUDA(dst, cudaMemcpyAsync(LD->dCopies.ptr, list.data(), sizeof(twl::RowCopy) * n, cudaMemcpyHostToDevice, dst->stream));
+    twl::rowTransferKernel<<<(n * 32 + 255) / 256, 256, 0, dst->stream>>>(LD->dCopies.ptr, n, LD->dStage.ptr, 1);
+    TWL_CUDA(dst, cudaGetLastError());
+    TWL_CUDA(dst, cudaStreamSynchronize(dst->stream));     // `list` is read by the copy above; the source staging buffer is free again
+    return twl_rows_drop(src, n, ids);
+}
+
 int twl_rows_lengths(twl_ctx *ctx, int n, const int32_t *ids, int32_t *lens) {
     if (!ctx || n < 0 || (n > 0 && (!ids || !lens))) return TWL_E_ARG;
     for (int i = 0; i < n; ++i) lens[i] = twl_rows_length(ctx, ids[i]);
@@ -797,12 +875,6 @@ int runLevelChunkImpl(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pair
             }
         });
     tr.mark("results to caller (host)");
-    // buffers that regrown rows left behind serve other rows from now on (everything that read them is stream-ordered before)
-    for (const RowUndo &u : journal) {
-        const RowSlot &r = L->rows[u.id];
-        if (r.buf[0] != u.buf[0]) { poolRecycle(L, u.buf[0], u.cap); poolRecycle(L, u.buf[1], u.cap); }
-    }
-    journal.clear();
     const bool updateTimed = nu > 0;
     for (int i = 0; i < 3; ++i) {
         float ms = 0.f;
@@ -819,20 +891,8 @@ int runLevelChunkImpl(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pair
 
 template <int P>
 int runLevelChunk(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pairs, int begin, int end, int task, float threshold,
-                  int cacheTh, int8_t *const *paths, twl_level_result *results, int chunkNo) {
-    std::vector<RowUndo> journal;
-    const int rc = runLevelChunkImpl<P>(ctx, L, pairs, begin, end, task, threshold, cacheTh, paths, results, chunkNo, journal);
-    if (rc != TWL_OK) {
-        // nothing of this chunk counts: rows point at their old buffers again (whatever was enqueued only wrote the other
-        // buffer of each row, or buffers that were freshly allocated and are dropped here)
-        cudaStreamSynchronize(ctx->stream);
-        for (auto it = journal.rbegin(); it != journal.rend(); ++it) {
-            RowSlot &r = L->rows[it->id];
-            r.buf[0] = it->buf[0]; r.buf[1] = it->buf[1]; r.cap = it->cap; r.storage = it->storage; r.len = it->len;
-        }
-        cudaGetLastError();
-    }
-    return rc;
+                  int cacheTh, int8_t *const *paths, twl_level_result *results, int chunkNo, std::vector<RowUndo> &journal) {
+    return runLevelChunkImpl<P>(ctx, L, pairs, begin, end, task, threshold, cacheTh, paths, results, chunkNo, journal);
 }
 
 } // namespace
@@ -856,6 +916,10 @@ int twl_align_level(twl_ctx *ctx, const twl_level_pair *pairs, int n_pairs, int 
     // chunk the level so that the scratch (raw profiles dominate: 4*P bytes per column and side) stays bounded
     size_t budget = static_cast<size_t>(12) << 30;
     if (const char *e = std::getenv("TWL_LEVEL_BUDGET_MB")) budget = static_cast<size_t>(std::max(1, std::atoi(e))) << 20;   // tests force small chunks
+    // The call is all or nothing for the row store: `journal` remembers every row a chunk touched; when any chunk fails
+    // (CUDA error, out of memory) every row points at its old buffers again (a chunk only ever writes the OTHER buffer of a
+    // row, or freshly allocated ones), so a caller that handles the error code finds the rows as they were before the call.
+    std::vector<RowUndo> journal;
     int begin = 0, chunkNo = 0;
     while (begin < n_pairs) {
         int end = begin;
@@ -867,11 +931,26 @@ int twl_align_level(twl_ctx *ctx, const twl_level_pair *pairs, int n_pairs, int 
             bytes += need;
             ++end;
         }
-        const int rc = (ctx->P == 6) ? runLevelChunk<6>(ctx, L, pairs, begin, end, current_task, gappy_threshold, cache_threshold, paths, results, chunkNo)
-                                     : runLevelChunk<22>(ctx, L, pairs, begin, end, current_task, gappy_threshold, cache_threshold, paths, results, chunkNo);
-        if (rc != TWL_OK) return rc;
+        const int rc = (ctx->P == 6) ? runLevelChunk<6>(ctx, L, pairs, begin, end, current_task, gappy_threshold, cache_threshold, paths, results, chunkNo, journal)
+                                     : runLevelChunk<22>(ctx, L, pairs, begin, end, current_task, gappy_threshold, cache_threshold, paths, results, chunkNo, journal);
+        if (rc != TWL_OK) {
+            const std::string why = ctx->error;
+            cudaStreamSynchronize(ctx->stream);
+            for (auto it = journal.rbegin(); it != journal.rend(); ++it) {
+                RowSlot &r = L->rows[it->id];
+                r.buf[0] = it->buf[0]; r.buf[1] = it->buf[1]; r.cap = it->cap; r.storage = it->storage; r.len = it->len;
+            }
+            cudaGetLastError();
+            ctx->error = why;
+            return rc;
+        }
         begin = end;
         ++chunkNo;
+    }
+    // buffers that regrown rows left behind serve other rows from now on (everything that read them is stream-ordered before)
+    for (const RowUndo &u : journal) {
+        const RowSlot &r = L->rows[u.id];
+        if (r.buf[0] != u.buf[0] && r.buf[1] != u.buf[0]) { poolRecycle(L, u.buf[0], u.cap); poolRecycle(L, u.buf[1], u.cap); }
     }
     L->lastChunks = chunkNo;
     float total = 0.f;

@@ -31,6 +31,8 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 namespace msa {
@@ -43,20 +45,28 @@ namespace b200 {
 
 namespace {
 
+// One context per GPU the run may use: TWL_DEVICES="0,1,2,3" (or "all"); default one device, TWL_DEVICE or 0. This is the
+// reference GPU build's --gpu-index / one-host-thread-per-GPU scheme (src/cuda/gpu-info.cu:6-94, alignment-gpu.cu:226-253)
+// with device-resident rows: every row lives on exactly one device at a time.
 struct Device {
     twl_ctx *ctx = nullptr;
+    int index = 0;
+};
+struct Devices {
+    std::vector<Device> dev;
     int M = 0;
     float gapOpen = 0, gapExtend = 0, gapBoundary = 0;
     std::vector<float> score;
 };
 
 // TWL_STATS=1: one JSON line on stderr at exit with what the device did for this run (bench.py reads it for the
-// BASELINE.json configs that go through the CLI): device milliseconds by phase, DP cell updates, pairs, levels,
-// bytes moved each way, and the wall time spent inside the level calls (host bookkeeping included).
+// BASELINE.json configs that go through the CLI): device milliseconds by phase (per level the slowest device counts), DP
+// cell updates, pairs, levels, bytes moved each way, and the wall time spent inside the level calls (host bookkeeping included).
 struct Stats {
     bool on = false;
     double phaseMs[4] = {0, 0, 0, 0}, wallMs = 0;
-    unsigned long long cells = 0, pairs = 0, levels = 0, h2dBytes = 0, d2hBytes = 0, deferred = 0;
+    unsigned long long cells = 0, pairs = 0, levels = 0, h2dBytes = 0, d2hBytes = 0, deferred = 0, migratedRows = 0;
+    std::vector<unsigned long long> pairsOnDevice;
 };
 Stats &stats() {
     static Stats s;
@@ -64,15 +74,19 @@ Stats &stats() {
 }
 void printStats() {
     const Stats &s = stats();
+    std::string per = "[";
+    for (size_t d = 0; d < s.pairsOnDevice.size(); ++d) per += (d ? ", " : "") + std::to_string(s.pairsOnDevice[d]);
+    per += "]";
     std::fprintf(stderr, "[twl-stats] {\"levels\": %llu, \"pairs\": %llu, \"deferred_pairs\": %llu, \"cells\": %llu, \"device_ms\": %.3f, "
                  "\"phase_ms\": {\"profile_build\": %.3f, \"gappy_psgp_pack\": %.3f, \"dp_chain\": %.3f, \"row_update_freq_merge\": %.3f}, "
-                 "\"level_calls_wall_ms\": %.3f, \"h2d_row_bytes\": %llu, \"d2h_row_bytes\": %llu}\n",
+                 "\"level_calls_wall_ms\": %.3f, \"h2d_row_bytes\": %llu, \"d2h_row_bytes\": %llu, \"devices\": %zu, \"pairs_per_device\": %s, "
+                 "\"rows_migrated_between_devices\": %llu}\n",
                  s.levels, s.pairs, s.deferred, s.cells, s.phaseMs[0] + s.phaseMs[1] + s.phaseMs[2] + s.phaseMs[3], s.phaseMs[0], s.phaseMs[1],
-                 s.phaseMs[2], s.phaseMs[3], s.wallMs, s.h2dBytes, s.d2hBytes);
+                 s.phaseMs[2], s.phaseMs[3], s.wallMs, s.h2dBytes, s.d2hBytes, s.pairsOnDevice.size(), per.c_str(), s.migratedRows);
 }
 
-Device &device() {
-    static Device d;
+Devices &devices() {
+    static Devices d;
     return d;
 }
 
@@ -81,67 +95,102 @@ Device &device() {
     std::exit(1);
 }
 
-void ensureContext(Params &param) {
-    Device &d = device();
-    if (!d.ctx) {
-        const char *env = std::getenv("TWL_DEVICE");
-        const int dev = env ? std::atoi(env) : 0;
-        if (twl_init(dev, &d.ctx) != TWL_OK) die("cannot initialise the CUDA device", twl_last_error(nullptr));
+void ensureContexts(Params &param) {
+    Devices &D = devices();
+    if (D.dev.empty()) {
+        std::vector<int> want;
+        if (const char *env = std::getenv("TWL_DEVICES")) {
+            const std::string all(env);
+            if (all == "all") {
+                for (int i = 0; i < twl_device_count(); ++i) want.push_back(i);
+            } else {
+                size_t at = 0;
+                while (at < all.size()) {
+                    const size_t end = std::min(all.find(',', at), all.size());
+                    if (end > at) want.push_back(std::atoi(all.substr(at, end - at).c_str()));
+                    at = end + 1;
+                }
+            }
+        }
+        if (want.empty()) {
+            const char *env = std::getenv("TWL_DEVICE");
+            want.push_back(env ? std::atoi(env) : 0);
+        }
+        for (int idx : want) {
+            Device d;
+            d.index = idx;
+            if (twl_init(idx, &d.ctx) != TWL_OK) die("cannot initialise the CUDA device", twl_last_error(nullptr));
+            D.dev.push_back(d);
+        }
         stats().on = std::getenv("TWL_STATS") != nullptr;
+        stats().pairsOnDevice.assign(D.dev.size(), 0);
         std::atexit([] {
             if (stats().on) printStats();
-            if (device().ctx) { twl_destroy(device().ctx); device().ctx = nullptr; }
+            for (Device &d : devices().dev) if (d.ctx) { twl_destroy(d.ctx); d.ctx = nullptr; }
         });
     }
     const int M = param.matrixSize;
     std::vector<float> flat(static_cast<size_t>(M) * M);
     for (int i = 0; i < M; ++i)
         for (int j = 0; j < M; ++j) flat[i * M + j] = param.scoringMatrix[i][j];
-    if (d.M != M || d.gapOpen != param.gapOpen || d.gapExtend != param.gapExtend || d.gapBoundary != param.gapBoundary || d.score != flat) {
-        if (twl_set_params(d.ctx, flat.data(), M, param.gapOpen, param.gapExtend, param.gapBoundary) != TWL_OK)
-            die("twl_set_params", twl_last_error(d.ctx));
-        d.M = M; d.gapOpen = param.gapOpen; d.gapExtend = param.gapExtend; d.gapBoundary = param.gapBoundary; d.score = flat;
+    if (D.M != M || D.gapOpen != param.gapOpen || D.gapExtend != param.gapExtend || D.gapBoundary != param.gapBoundary || D.score != flat) {
+        for (Device &d : D.dev)
+            if (twl_set_params(d.ctx, flat.data(), M, param.gapOpen, param.gapExtend, param.gapBoundary) != TWL_OK)
+                die("twl_set_params", twl_last_error(d.ctx));
+        D.M = M; D.gapOpen = param.gapOpen; D.gapExtend = param.gapExtend; D.gapBoundary = param.gapBoundary; D.score = flat;
     }
 }
 
 // Where the current text of a row lives. Within one msaOnSubtree call the host never writes a member row between
 // levels (the only host writer, progressive::updateAlignment, runs after the last level and only touches parked rows),
 // so residency is tracked by generation: beginSubtree() forgets everything, a row is uploaded the first time a level
-// needs it, and `dirty` means the device holds a newer text than SequenceInfo::alnStorage.
+// needs it, and `dirty` means a device holds a newer text than SequenceInfo::alnStorage.
 struct Resident {
-    bool onDevice = false, dirty = false;
+    int8_t dev = -1;         // device slot that holds the row, -1: host only
+    int8_t home = -1;        // preferred device slot of a leaf (contiguous blocks of the guide tree's leaf order), -1: none
+    bool dirty = false;
 };
 struct RowState {
     SequenceDB *db = nullptr;
     std::vector<Resident> rows;
     size_t nDirty = 0;
+    bool homesReady = false;
 };
 RowState &rowState() {
     static RowState r;
     return r;
 }
+Resident &residentOf(int id, SequenceDB *database) {
+    RowState &rs = rowState();
+    if (static_cast<size_t>(id) >= rs.rows.size()) rs.rows.resize(std::max<size_t>(id + 1, database->sequences.size()));
+    return rs.rows[id];
+}
 
-// device rows -> SequenceInfo::alnStorage[storage] for the given ids (all of them dirty), in bounded slices
+// device rows -> SequenceInfo::alnStorage[storage] for the given ids (all resident), per device and in bounded slices
 void downloadRows(SequenceDB *database, const std::vector<int32_t> &ids) {
     if (ids.empty()) return;
-    twl_ctx *ctx = device().ctx;
     RowState &rs = rowState();
+    Devices &D = devices();
     constexpr size_t kSliceBytes = static_cast<size_t>(512) << 20;
-    size_t at = 0;
-    while (at < ids.size()) {
-        size_t end = at, bytes = 0;
-        std::vector<char *> dst;
-        while (end < ids.size() && (end == at || bytes < kSliceBytes)) {
-            auto *seq = database->sequences[ids[end]];
-            seq->memCheck(seq->len);                                       // sequencedb.cpp:57-76 (host len already tracks the device)
-            dst.push_back(seq->alnStorage[seq->storage]);
-            bytes += static_cast<size_t>(seq->len);
-            ++end;
+    for (size_t d = 0; d < D.dev.size(); ++d) {
+        std::vector<int32_t> mine;
+        for (int32_t id : ids) if (rs.rows[id].dev == static_cast<int8_t>(d)) mine.push_back(id);
+        size_t at = 0;
+        while (at < mine.size()) {
+            size_t end = at, bytes = 0;
+            std::vector<char *> dst;
+            while (end < mine.size() && (end == at || bytes < kSliceBytes)) {
+                auto *seq = database->sequences[mine[end]];
+                seq->memCheck(seq->len);                                   // sequencedb.cpp:57-76 (host len already tracks the device)
+                dst.push_back(seq->alnStorage[seq->storage]);
+                bytes += static_cast<size_t>(seq->len);
+                ++end;
+            }
+            stats().d2hBytes += bytes;
+            if (twl_rows_download(D.dev[d].ctx, static_cast<int>(end - at), mine.data() + at, dst.data(), nullptr) != TWL_OK)
+                die("twl_rows_download", twl_last_error(D.dev[d].ctx));
+            at = end;
         }
-        stats().d2hBytes += bytes;
-        if (twl_rows_download(ctx, static_cast<int>(end - at), ids.data() + at, dst.data(), nullptr) != TWL_OK)
-            die("twl_rows_download", twl_last_error(ctx));
-        at = end;
     }
     for (int32_t id : ids)
         if (rs.rows[id].dirty) { rs.rows[id].dirty = false; --rs.nDirty; }
@@ -175,28 +224,54 @@ bool fetchFreq(twl_ctx *ctx, int pair, int what, std::vector<float> &out) {
     return twl_level_fetch(ctx, pair, what, out.data(), bytes, &bytes) == TWL_OK;
 }
 
+// Leaves of the guide tree in depth-first order get contiguous blocks of devices as their "home": sibling subtrees then
+// meet on one device and only the few joins near the root move rows between GPUs (subtree-affine placement).
+void assignHomes(Tree *tree, SequenceDB *database) {
+    RowState &rs = rowState();
+    rs.homesReady = true;
+    const size_t nDev = devices().dev.size();
+    if (nDev < 2 || !tree || !tree->root) return;
+    std::vector<int> leafIds;
+    std::vector<Node *> stack{tree->root};
+    while (!stack.empty()) {
+        Node *nd = stack.back();
+        stack.pop_back();
+        if (nd->children.empty()) {
+            auto it = database->name_map.find(nd->identifier);
+            if (it != database->name_map.end()) leafIds.push_back(it->second->id);
+            continue;
+        }
+        for (auto c = nd->children.rbegin(); c != nd->children.rend(); ++c) stack.push_back(*c);
+    }
+    for (size_t k = 0; k < leafIds.size(); ++k) residentOf(leafIds[k], database).home = static_cast<int8_t>(k * nDev / leafIds.size());
+}
+
 } // namespace
 
-// A new SequenceDB generation: the device row store is emptied (its pools are kept for reuse) and nothing is assumed
+// A new SequenceDB generation: the device row stores are emptied (their pools are kept for reuse) and nothing is assumed
 // resident. Called by the msaOnSubtree wrapper below, i.e. once per subtree / merge pass.
 void beginSubtree(SequenceDB *database) {
     RowState &rs = rowState();
-    if (device().ctx && twl_rows_clear(device().ctx) != TWL_OK) die("twl_rows_clear", twl_last_error(device().ctx));
+    for (Device &d : devices().dev)
+        if (d.ctx && twl_rows_clear(d.ctx) != TWL_OK) die("twl_rows_clear", twl_last_error(d.ctx));
     rs.db = database;
     rs.rows.clear();
     rs.nDirty = 0;
+    rs.homesReady = false;
 }
 
-// Every row the device rewrote and the host has not seen yet goes back into the SequenceDB, so that everything after
+// Every row a device rewrote and the host has not seen yet goes back into the SequenceDB, so that everything after
 // msaOnSubtree (storeSubtreeProfile, writeSubAlignments, writeFinalMSA, --check) reads the same bytes as after the CPU path.
 void endSubtree(SequenceDB *database) { downloadAllDirty(database); }
 
 void alignmentKernel_B200_level(Tree *tree, NodePairVec &nodes, SequenceDB *database, Option *option, Params &param) {
-    ensureContext(param);
-    twl_ctx *ctx = device().ctx;
+    ensureContexts(param);
+    Devices &D = devices();
+    const int nDev = static_cast<int>(D.dev.size());
     RowState &rs = rowState();
     const auto wall0 = std::chrono::steady_clock::now();
     if (rs.db != database) beginSubtree(database);                         // called outside the msaOnSubtree wrapper
+    if (!rs.homesReady) assignHomes(tree, database);
     const int P = param.matrixSize + 1;
     const int task = database->currentTask;
     const int nPairs = static_cast<int>(nodes.size());
@@ -205,12 +280,9 @@ void alignmentKernel_B200_level(Tree *tree, NodePairVec &nodes, SequenceDB *data
     std::vector<std::vector<int32_t>> ids(2 * nPairs);
     std::vector<std::vector<float>> freqs(2 * nPairs);
     std::vector<char> lowQ(nPairs, 0), needPath(nPairs, 0);
+    std::vector<int> devOf(nPairs, 0), localIdx(nPairs, 0);
     const bool updateRows = (option->alnMode != PLACE_WO_TREE) && (task != 2);
 
-    // rows the device does not hold yet
-    std::vector<int32_t> upIds, upLens;
-    std::vector<const char *> upRows;
-    std::vector<float> upW;
     for (int n = 0; n < nPairs; ++n) {
         Node *nd[2] = {nodes[n].first, nodes[n].second};
         twl_node_side *side[2] = {&lp[n].ref, &lp[n].qry};
@@ -221,13 +293,6 @@ void alignmentKernel_B200_level(Tree *tree, NodePairVec &nodes, SequenceDB *data
                 if (sIdx < 0) { needPath[n] = 1; continue; }               // parked group / subtree id: path composition only
                 if (cached && !updateRows) continue;                       // rows neither read nor written
                 v.push_back(sIdx);
-                if (static_cast<size_t>(sIdx) >= rs.rows.size()) rs.rows.resize(std::max<size_t>(sIdx + 1, database->sequences.size()));
-                Resident &r = rs.rows[sIdx];
-                if (!r.onDevice) {
-                    auto *seq = database->sequences[sIdx];
-                    upIds.push_back(sIdx); upLens.push_back(seq->len); upRows.push_back(seq->alnStorage[seq->storage]); upW.push_back(seq->weight);
-                    r.onDevice = true;
-                }
             }
             if (cached) flatten(nd[s]->msaFreq, freqs[2 * n + s]);
             side[s]->seq_ids = v.data();
@@ -246,56 +311,137 @@ void alignmentKernel_B200_level(Tree *tree, NodePairVec &nodes, SequenceDB *data
         if (option->alnMode == PLACE_WO_TREE || task == 2) needPath[n] = 1;
     }
 
+    // ---- which device aligns which pair: where most of its rows already are; for rows nobody holds yet, the home of the
+    // pair's first leaf; otherwise the device with the least work so far in this level
+    std::vector<double> load(nDev, 0.0);
+    if (nDev > 1) {
+        for (int n = 0; n < nPairs; ++n) {
+            std::vector<double> bytes(nDev, 0.0);
+            int home = -1;
+            bool any = false;
+            for (int s = 0; s < 2; ++s)
+                for (int32_t id : ids[2 * n + s]) {
+                    const Resident &r = residentOf(id, database);
+                    if (r.dev >= 0) { bytes[r.dev] += database->sequences[id]->len + 1; any = true; }
+                    else if (home < 0) home = r.home;
+                }
+            int d = 0;
+            if (any) d = static_cast<int>(std::max_element(bytes.begin(), bytes.end()) - bytes.begin());
+            else if (home >= 0) d = home;
+            else d = static_cast<int>(std::min_element(load.begin(), load.end()) - load.begin());
+            devOf[n] = d;
+            load[d] += static_cast<double>(lp[n].ref.aln_len) + lp[n].qry.aln_len;
+        }
+    }
+
     // the final path comes back to the host only where the host composes paths with it (negative ids, PLACE_WO_TREE, merges)
     std::vector<twl_level_result> out(nPairs);
     std::vector<std::vector<int8_t>> pathBuf(nPairs);
-    std::vector<int8_t *> pathPtr(nPairs, nullptr);
     for (int n = 0; n < nPairs; ++n)
-        if (needPath[n]) {
-            pathBuf[n].resize(static_cast<size_t>(lp[n].ref.aln_len) + lp[n].qry.aln_len + 1);
-            pathPtr[n] = pathBuf[n].data();
-        }
+        if (needPath[n]) pathBuf[n].resize(static_cast<size_t>(lp[n].ref.aln_len) + lp[n].qry.aln_len + 1);
 
-    // One retry when the device runs out of memory: everything the device holds goes back to the host, the row store is
+    struct PerDevice {
+        std::vector<int> pairs;                       // indices into `nodes`
+        std::vector<twl_level_pair> lp;
+        std::vector<int8_t *> paths;
+        std::vector<twl_level_result> out;
+        std::vector<int32_t> upIds, upLens;
+        std::vector<const char *> upRows;
+        std::vector<float> upW;
+        int rc = TWL_OK;
+        float phase[4] = {0, 0, 0, 0};
+    };
+    // One retry when a device runs out of memory: everything the devices hold goes back to the host, the row stores are
     // emptied and the level's rows are sent again (inputs larger than HBM degrade to per-level staging instead of failing).
     for (int attempt = 0;; ++attempt) {
-        int rc = TWL_OK;
-        if (!upIds.empty()) rc = twl_rows_upload(ctx, static_cast<int>(upIds.size()), upIds.data(), upRows.data(), upLens.data(), upW.data());
-        if (rc == TWL_OK) rc = twl_align_level(ctx, lp.data(), nPairs, task, option->gappyVertical, alignment_helper::_CAL_PROFILE_TH, pathPtr.data(), out.data());
-        if (rc == TWL_OK) break;
-        if (rc != TWL_E_NOMEM || attempt > 0) die("twl_align_level", twl_last_error(ctx));
-        std::cerr << "twilight-b200: device memory exhausted, spilling the row store to the host and retrying the level\n";
-        downloadAllDirty(database);
-        beginSubtree(database);
-        upIds.clear(); upLens.clear(); upRows.clear(); upW.clear();
-        for (auto &v : ids)
-            for (int32_t sIdx : v) {
-                if (static_cast<size_t>(sIdx) >= rs.rows.size()) rs.rows.resize(std::max<size_t>(sIdx + 1, database->sequences.size()));
-                if (rs.rows[sIdx].onDevice) continue;
-                auto *seq = database->sequences[sIdx];
-                upIds.push_back(sIdx); upLens.push_back(seq->len); upRows.push_back(seq->alnStorage[seq->storage]); upW.push_back(seq->weight);
-                rs.rows[sIdx].onDevice = true;
+        std::vector<PerDevice> pd(nDev);
+        std::vector<std::vector<std::vector<int32_t>>> moves(nDev, std::vector<std::vector<int32_t>>(nDev));   // [from][to] -> row ids
+        for (int n = 0; n < nPairs; ++n) {
+            PerDevice &p = pd[devOf[n]];
+            localIdx[n] = static_cast<int>(p.pairs.size());
+            p.pairs.push_back(n);
+            p.lp.push_back(lp[n]);
+            p.paths.push_back(needPath[n] ? pathBuf[n].data() : nullptr);
+            for (int s = 0; s < 2; ++s)
+                for (int32_t id : ids[2 * n + s]) {
+                    Resident &r = residentOf(id, database);
+                    if (r.dev == devOf[n]) continue;
+                    if (r.dev >= 0) moves[r.dev][devOf[n]].push_back(id);
+                    else {
+                        auto *seq = database->sequences[id];
+                        p.upIds.push_back(id); p.upLens.push_back(seq->len); p.upRows.push_back(seq->alnStorage[seq->storage]); p.upW.push_back(seq->weight);
+                    }
+                    r.dev = static_cast<int8_t>(devOf[n]);
+                }
+        }
+        // rows that change device: GPU to GPU (twl_rows_migrate: cudaMemcpyPeer over NVLink), at most a few joins per level
+        for (int a = 0; a < nDev; ++a)
+            for (int b = 0; b < nDev; ++b)
+                if (!moves[a][b].empty()) {
+                    if (twl_rows_migrate(D.dev[a].ctx, D.dev[b].ctx, static_cast<int>(moves[a][b].size()), moves[a][b].data()) != TWL_OK)
+                        die("twl_rows_migrate", twl_last_error(D.dev[b].ctx));
+                    stats().migratedRows += moves[a][b].size();
+                }
+        auto runDevice = [&](int d) {
+            PerDevice &p = pd[d];
+            if (p.pairs.empty()) return;
+            p.out.resize(p.pairs.size());
+            twl_ctx *ctx = D.dev[d].ctx;
+            if (!p.upIds.empty()) p.rc = twl_rows_upload(ctx, static_cast<int>(p.upIds.size()), p.upIds.data(), p.upRows.data(), p.upLens.data(), p.upW.data());
+            if (p.rc == TWL_OK)
+                p.rc = twl_align_level(ctx, p.lp.data(), static_cast<int>(p.lp.size()), task, option->gappyVertical, alignment_helper::_CAL_PROFILE_TH, p.paths.data(), p.out.data());
+            if (p.rc == TWL_OK) twl_level_phase_ms(ctx, p.phase);
+        };
+        // one host thread per GPU, as the reference GPU build (alignment-gpu.cu:247)
+        std::vector<std::thread> workers;
+        for (int d = 1; d < nDev; ++d) if (!pd[d].pairs.empty()) workers.emplace_back(runDevice, d);
+        runDevice(0);
+        for (auto &w : workers) w.join();
+        bool nomem = false, failed = false;
+        for (int d = 0; d < nDev; ++d) {
+            if (pd[d].rc == TWL_E_NOMEM) nomem = true;
+            else if (pd[d].rc != TWL_OK) { failed = true; std::cerr << "twilight-b200: device " << D.dev[d].index << ": " << twl_last_error(D.dev[d].ctx) << "\n"; }
+        }
+        // (with several devices a level may have completed on some of them: no clean retry; twl_align_level itself is all or nothing)
+        if (failed || (nomem && (attempt > 0 || nDev > 1))) die("twl_align_level", nomem ? "out of device memory" : "failed");
+        if (nomem) {
+            std::cerr << "twilight-b200: device memory exhausted, spilling the row stores to the host and retrying the level\n";
+            // rows of devices whose call did not run keep their content; everything goes back to the host and is forgotten
+            downloadAllDirty(database);
+            beginSubtree(database);
+            rs.homesReady = true;
+            continue;
+        }
+        for (int d = 0; d < nDev; ++d)
+            for (size_t k = 0; k < pd[d].pairs.size(); ++k) out[pd[d].pairs[k]] = pd[d].out[k];
+        if (stats().on) {
+            Stats &st = stats();
+            for (int i = 0; i < 4; ++i) {
+                float m = 0.f;
+                for (int d = 0; d < nDev; ++d) m = std::max(m, pd[d].phase[i]);
+                st.phaseMs[i] += m;
             }
+            st.levels += 1;
+            st.pairs += static_cast<unsigned long long>(nPairs);
+            for (int n = 0; n < nPairs; ++n) st.cells += out[n].cells;
+            for (int d = 0; d < nDev; ++d) {
+                st.pairsOnDevice[d] += pd[d].pairs.size();
+                for (int32_t len : pd[d].upLens) st.h2dBytes += static_cast<unsigned long long>(len);
+            }
+        }
+        break;
     }
 
-    if (stats().on) {
-        Stats &st = stats();
-        float ph[4] = {0, 0, 0, 0};
-        twl_level_phase_ms(ctx, ph);
-        for (int i = 0; i < 4; ++i) st.phaseMs[i] += ph[i];
-        st.levels += 1;
-        st.pairs += static_cast<unsigned long long>(nPairs);
-        for (int n = 0; n < nPairs; ++n) st.cells += out[n].cells;
-        for (int32_t len : upLens) st.h2dBytes += static_cast<unsigned long long>(len);
-    }
     std::vector<int> fallbackPairs;
     std::vector<int32_t> parkedIds;
     for (int n = 0; n < nPairs; ++n) {
         Node *first = nodes[n].first, *second = nodes[n].second;
+        twl_ctx *ctx = D.dev[devOf[n]].ctx;
+        const int ln = localIdx[n];
         std::vector<float> flat;
         // calculateProfile's msaFreq cache (helper.cpp:35-40) happens whether or not the pair aligns
-        if ((out[n].cached & 1) && fetchFreq(ctx, n, TWL_F_FREQ_REF, flat)) unflatten(flat, P, first->msaFreq);
-        if ((out[n].cached & 2) && fetchFreq(ctx, n, TWL_F_FREQ_QRY, flat)) unflatten(flat, P, second->msaFreq);
+        if ((out[n].cached & 1) && fetchFreq(ctx, ln, TWL_F_FREQ_REF, flat)) unflatten(flat, P, first->msaFreq);
+        if ((out[n].cached & 2) && fetchFreq(ctx, ln, TWL_F_FREQ_QRY, flat)) unflatten(flat, P, second->msaFreq);
         const int refNum = lp[n].ref.aln_num, qryNum = lp[n].qry.aln_num;
         if (!lowQ[n] && out[n].status != 0) {
             if (out[n].status == 3) { std::cout << "There might be some bugs in the code!\n"; std::exit(1); }
@@ -313,7 +459,7 @@ void alignmentKernel_B200_level(Tree *tree, NodePairVec &nodes, SequenceDB *data
         }
         // updateFrequency, helper.cpp:506-539
         if (!first->msaFreq.empty() && !second->msaFreq.empty()) {
-            if (!(out[n].cached & 4) || !fetchFreq(ctx, n, TWL_F_FREQ_MERGED, flat)) die("twl_level_fetch", "merged msaFreq missing");
+            if (!(out[n].cached & 4) || !fetchFreq(ctx, ln, TWL_F_FREQ_MERGED, flat)) die("twl_level_fetch", "merged msaFreq missing");
             second->msaFreq.clear();
             unflatten(flat, P, first->msaFreq);
             first->alnLen = static_cast<int>(first->msaFreq.size());
