@@ -173,6 +173,9 @@ int twl_level_fetch(twl_ctx *ctx, int pair, int what, void *dst, size_t cap_byte
 /* Device time of the last twl_align_level call by phase, milliseconds: [0] profile build, [1] gappy/PSGP/pack,
  * [2] DP chain, [3] row update + frequency merge. */
 int twl_level_phase_ms(twl_ctx *ctx, float out[4]);
+/* Phase [3] split in two: out[0] = gappy-column restore (addGappyColumnsBack: a sequential merge per pair, latency bound),
+ * out[1] = path prefix counts + row rewrite + frequency merge (updateAlignment / updateFrequency: the HBM-bound part). */
+int twl_level_update_split_ms(twl_ctx *ctx, float out[2]);
 
 /* addGappyColumnsBack (alignment-helper.cpp:324-375) runs on the device. When removed runs of BOTH nodes start at the same
  * path position the reference aligns their consensus substrings (pairwiseGlobal, alignment-helper.cpp:243-322); the kernel

@@ -113,3 +113,13 @@ def test_two_rank_sharded_msa_equals_single_process(tmp_path):
     rows1, st1 = msa.progressive_align(FakeContext(), tree, seqs, w)
     assert aln_len2 == st1.aln_len
     assert rows2 == rows1
+
+
+def test_subtree_affinity_on_a_deep_unbalanced_tree():
+    """A caterpillar guide tree of 5000 leaves is 4999 levels deep: the partition must not recurse."""
+    from twilight_b200 import shard, synth
+    tree = synth.random_tree(5000, seed=3, shape="caterpillar")
+    levels = synth.levels_bottom_up(tree)
+    owner = shard.subtree_affinity(levels, 4, tree.n_nodes)
+    assert (owner >= 0).all() and set(owner[:5000].tolist()) <= {0, 1, 2, 3}
+    assert owner[tree.root] >= 0

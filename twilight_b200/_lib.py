@@ -66,6 +66,7 @@ SIGNATURES = {
     "twl_align_level": (C.c_int, [C.c_void_p, C.POINTER(LevelPair), C.c_int, C.c_int, C.c_float, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(LevelResult)]),
     "twl_level_fetch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "twl_level_phase_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "twl_level_update_split_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "twl_level_large_restores": (C.c_int, [C.c_void_p]),
     "twl_last_kernel_ms": (C.c_float, [C.c_void_p]),
     "twl_last_launch_count": (C.c_int, [C.c_void_p]),
@@ -85,6 +86,8 @@ def load():
                                "(there is no fallback implementation)")
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
+            if os.environ.get("TWL_LIB") and not hasattr(lib, name):
+                continue          # an older build given for A/B timing may lack newer entry points
             fn = getattr(lib, name)   # AttributeError if the library does not export a declared symbol
             fn.restype = res
             fn.argtypes = args

@@ -402,6 +402,12 @@ class Context:
         width = self.P + 2 if what in F_DP_PROFILE else self.P
         return out.reshape(-1, width)
 
+    def level_update_split_ms(self):
+        """(gappy-column restore ms, path counts + row rewrite + frequency merge ms) of the last align_level call."""
+        out = (C.c_float * 2)()
+        self._check(self._lib.twl_level_update_split_ms(self._h, out))
+        return [float(out[0]), float(out[1])]
+
     def level_phase_ms(self):
         out = (C.c_float * 4)()
         self._check(self._lib.twl_level_phase_ms(self._h, out))

@@ -109,6 +109,119 @@ __global__ void __launch_bounds__(kLvlThreads) profileBuildKernel(const DevSide 
     cons[sd.consOff + t] = lut[best];
 }
 
+// Nucleotide version (P = 6) of the same computation for the HBM roofline: a thread owns FOUR consecutive columns, reads
+// each member row with one 32-bit load (rows are 16-byte aligned and over-allocated, so the word that holds the last
+// columns may be read whole), and writes its 24 profile floats with six 16-byte stores (the side's raw offset is a multiple
+// of four floats). Accumulation per column is still member by member in seqsIncluded order; the letter index comes from a
+// 256-entry table in shared memory. Also emits the per-column gap counts as a compact float array for the compaction pass.
+constexpr int kProfThreads = 128;
+constexpr int kProfCols = 4;
+__global__ void __launch_bounds__(kProfThreads) profileBuildNtKernel(const DevSide *sides, const char *const *rowPtr, const float *rowWeight,
+                                                                      float *raw, char *cons, const float *freqIn, float *freqOut, float *gapCount) {
+    constexpr int P = 6;
+    __shared__ float acc[P][kProfCols][kProfThreads];
+    __shared__ unsigned char lut[256];
+    const DevSide sd = sides[blockIdx.x];
+    const int t0 = (blockIdx.y * kProfThreads + threadIdx.x) * kProfCols;     // first of this thread's columns
+    if (blockIdx.y * kProfThreads * kProfCols >= sd.alnLen) return;
+    for (int c = threadIdx.x; c < 256; c += kProfThreads) lut[c] = static_cast<unsigned char>(letterIndexNt(static_cast<unsigned char>(c)));
+    const int nHere = min(kProfCols, sd.alnLen - t0);                          // <= 0: nothing to do for this thread
+    float col[kProfCols][P];
+    if (sd.freqInOff >= 0) {                                               // helper.cpp:16-21
+#pragma unroll
+        for (int c = 0; c < kProfCols; ++c)
+#pragma unroll
+            for (int v = 0; v < P; ++v)
+                col[c][v] = (c < nHere) ? __fmul_rn(__fdiv_rn(freqIn[sd.freqInOff + static_cast<long long>(t0 + c) * P + v], sd.nodeWeight), static_cast<float>(sd.alnNum)) : 0.0f;
+        __syncthreads();
+    } else {                                                               // helper.cpp:23-34
+#pragma unroll
+        for (int v = 0; v < P; ++v)
+#pragma unroll
+            for (int c = 0; c < kProfCols; ++c) acc[v][c][threadIdx.x] = 0.0f;
+        __syncthreads();
+        const char *const *rows = rowPtr + sd.memberOff;
+        const float *wts = rowWeight + sd.memberOff;
+        const float numF = static_cast<float>(sd.alnNum);
+        if (nHere > 0) {
+            int s = 0;
+            for (; s + 4 <= sd.nRows; s += 4) {                            // four member rows in flight
+                unsigned w4[4];
+                float ww[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    w4[u] = __ldg(reinterpret_cast<const unsigned *>(rows[s + u] + t0));
+                    ww[u] = __fmul_rn(__fdiv_rn(wts[s + u], sd.nodeWeight), numF);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int c = 0; c < kProfCols; ++c) {
+                        float *a = &acc[lut[(w4[u] >> (8 * c)) & 0xFFu]][c][threadIdx.x];
+                        *a = __fadd_rn(*a, ww[u]);
+                    }
+            }
+            for (; s < sd.nRows; ++s) {
+                const unsigned w4 = __ldg(reinterpret_cast<const unsigned *>(rows[s] + t0));
+                const float ww = __fmul_rn(__fdiv_rn(wts[s], sd.nodeWeight), numF);
+#pragma unroll
+                for (int c = 0; c < kProfCols; ++c) {
+                    float *a = &acc[lut[(w4 >> (8 * c)) & 0xFFu]][c][threadIdx.x];
+                    *a = __fadd_rn(*a, ww);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < kProfCols; ++c)
+#pragma unroll
+            for (int v = 0; v < P; ++v) col[c][v] = acc[v][c][threadIdx.x];
+    }
+    if (nHere <= 0) return;
+    float *dst = raw + sd.rawOff + static_cast<long long>(t0) * P;
+    float *fdst = (sd.freqOutOff >= 0) ? freqOut + sd.freqOutOff + static_cast<long long>(t0) * P : nullptr;
+    const char *letters = "ACGTN";
+    if (nHere == kProfCols) {
+        float4 *d4 = reinterpret_cast<float4 *>(dst);
+        const float *flat = &col[0][0];
+#pragma unroll
+        for (int x = 0; x < 6; ++x) d4[x] = make_float4(flat[4 * x], flat[4 * x + 1], flat[4 * x + 2], flat[4 * x + 3]);
+        if (fdst) {                                                        // helper.cpp:35-40
+#pragma unroll
+            for (int x = 0; x < 24; ++x) fdst[x] = __fmul_rn(__fdiv_rn(flat[x], static_cast<float>(sd.alnNum)), sd.nodeWeight);
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < kProfCols; ++c)
+#pragma unroll
+            for (int v = 0; v < P; ++v)
+                if (c < nHere) {
+                    dst[c * P + v] = col[c][v];
+                    if (fdst) fdst[c * P + v] = __fmul_rn(__fdiv_rn(col[c][v], static_cast<float>(sd.alnNum)), sd.nodeWeight);
+                }
+    }
+    // getConsensus, helper.cpp:221-241, and the gap counts for the compaction pass
+    unsigned packed = 0;
+    float g4[kProfCols];
+#pragma unroll
+    for (int c = 0; c < kProfCols; ++c) {
+        int best = P - 2;
+        float top = 0.0f;
+#pragma unroll
+        for (int v = 0; v < P - 2; ++v)
+            if (col[c][v] > top) { top = col[c][v]; best = v; }
+        packed |= static_cast<unsigned>(static_cast<unsigned char>(letters[best])) << (8 * c);
+        g4[c] = col[c][P - 1];
+    }
+    if (nHere == kProfCols) {
+        *reinterpret_cast<unsigned *>(cons + sd.consOff + t0) = packed;
+        *reinterpret_cast<float4 *>(gapCount + sd.consOff + t0) = make_float4(g4[0], g4[1], g4[2], g4[3]);
+    } else {
+#pragma unroll
+        for (int c = 0; c < kProfCols; ++c)
+            if (c < nHere) { cons[sd.consOff + t0 + c] = static_cast<char>((packed >> (8 * c)) & 0xFFu); gapCount[sd.consOff + t0 + c] = g4[c]; }
+    }
+}
+
 // Batched row transfers: rows sit at arbitrary places of the row pools, the host side of a transfer is one tightly packed
 // staging buffer. One warp copies one row (16-byte vectors when both ends allow it).
 struct RowCopy {
@@ -261,6 +374,132 @@ __global__ void __launch_bounds__(kLvlThreads) gappyCompactKernel(DevSide *sides
         if (P == 6 && allOneHot && newLen > 0) atomicOr(&pr.pad, sd.isQry ? kQryOneHot : kRefOneHot);   // DP fast path, talco_wavefront.cu
     }
     (void)sTotal;
+}
+
+// Nucleotide version (P = 6) for the HBM roofline: the gappy test reads the compact gap-count array profileBuildNtKernel wrote
+// (4 bytes per column instead of a strided pass over the raw profile), a thread owns four consecutive columns per 1024-column
+// chunk (one pair of block scans per chunk instead of per 256 columns), the raw columns come in as six 16-byte loads.
+// Same arithmetic, same outputs (DP layout, run list, newLen, one-hot flag) as gappyCompactKernel<6>.
+__global__ void __launch_bounds__(kLvlThreads) gappyCompactNtKernel(DevSide *sides, const float *raw, const float *gapCount, float *prof, int *runs,
+                                                                     DevPair *pairs, float threshold, float gapOpen, float gapExtend) {
+    constexpr int P = 6, C = 4;
+    __shared__ int warpSums[kLvlThreads / 32];
+    DevSide &sdRef = sides[blockIdx.x];
+    const DevSide sd = sdRef;
+    const float *col = raw + sd.rawOff;
+    const float *gc = gapCount + sd.consOff;
+    const bool enabled = (threshold != 1.0f);                               // helper.cpp:77
+    const float numF = static_cast<float>(sd.alnNum);
+    // helper.cpp:84 tests g / num > threshold with a float division per column. The quotient is monotonic in g, so the test is
+    // the same as g >= gMin with gMin the smallest float whose quotient exceeds the threshold: found once per side by stepping a
+    // few ulps around threshold * num with the very division the reference does (gap counts are >= 0).
+    float gMin;
+    {
+        float c = fmaxf(__fmul_rn(threshold, numF), 0.0f);
+        for (int it = 0; it < 64 && c > 0.0f && __fdiv_rn(c, numF) > threshold; ++it) c = __uint_as_float(__float_as_uint(c) - 1u);   // down to a failing value (or 0)
+        for (int it = 0; it < 128 && !(__fdiv_rn(c, numF) > threshold); ++it) c = __uint_as_float(__float_as_uint(c) + 1u);            // up to the first passing one
+        gMin = c;
+        if (!(__fdiv_rn(c, numF) > threshold) || (c > 0.0f && __fdiv_rn(__uint_as_float(__float_as_uint(c) - 1u), numF) > threshold)) gMin = -1.0f;   // not bracketed: divide per column
+    }
+    auto isGappy = [&](float g) { return enabled && ((gMin >= 0.0f) ? (g >= gMin) : (__fdiv_rn(g, numF) > threshold)); };
+
+    int kept = 0;
+    for (int t = threadIdx.x; t < sd.alnLen; t += kLvlThreads) kept += isGappy(gc[t]) ? 0 : 1;
+    int total;
+    blockExclusiveScan(kept, warpSums, &total);
+    const int newLen = total;
+    const int n4 = (newLen + 3) / 4;
+    float4 *outX = reinterpret_cast<float4 *>(prof + sd.profOff);
+    float4 *outY = outX + 4 * static_cast<long long>(n4);
+    int *r = runs + sd.runsOff;
+
+    const float minExtend = static_cast<float>(static_cast<double>(gapExtend) * 0.2);   // helper.cpp:180-181
+    const float minOpen = static_cast<float>(static_cast<double>(gapOpen) * 0.1);
+    const float openScaled = __fmul_rn(gapOpen, 0.5f);                      // helper.cpp:179 (nucleotide scale)
+
+    int keptBase = 0, runBase = 0;
+    bool oneHot = true;
+    for (int c0 = 0; c0 < sd.alnLen; c0 += kLvlThreads * C) {
+        const int t0 = c0 + threadIdx.x * C;
+        const int nHere = max(0, min(C, sd.alnLen - t0));
+        float g[C];
+        bool gp[C];
+        if (nHere == C) {
+            const float4 g4 = *reinterpret_cast<const float4 *>(gc + t0);
+            g[0] = g4.x; g[1] = g4.y; g[2] = g4.z; g[3] = g4.w;
+        } else {
+#pragma unroll
+            for (int c = 0; c < C; ++c) g[c] = (c < nHere) ? gc[t0 + c] : 0.0f;
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) gp[c] = (c < nHere) && isGappy(g[c]);
+        const bool prevG = (nHere > 0 && t0 > 0) && isGappy(gc[t0 - 1]);
+        const bool nextG = (t0 + C < sd.alnLen) && isGappy(gc[t0 + C]);
+        int nKept = 0, nStart = 0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            nKept += (c < nHere && !gp[c]) ? 1 : 0;
+            nStart += (gp[c] && !(c ? gp[c - 1] : prevG)) ? 1 : 0;
+        }
+        int chunkKept, chunkStarts;
+        int idx = keptBase + blockExclusiveScan(nKept, warpSums, &chunkKept);
+        int runIdx = runBase + blockExclusiveScan(nStart, warpSums, &chunkStarts);   // run starts before this thread's columns
+        float v[C][P];
+        if (nHere == C) {
+            const float4 *src = reinterpret_cast<const float4 *>(col + static_cast<long long>(t0) * P);
+            float *flat = &v[0][0];
+#pragma unroll
+            for (int x = 0; x < 6; ++x) { const float4 q = src[x]; flat[4 * x] = q.x; flat[4 * x + 1] = q.y; flat[4 * x + 2] = q.z; flat[4 * x + 3] = q.w; }
+        } else {
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int x = 0; x < P; ++x) v[c][x] = (c < nHere) ? col[static_cast<long long>(t0 + c) * P + x] : 0.0f;
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            if (c >= nHere) continue;
+            const int t = t0 + c;
+            if (!gp[c]) {
+                int ones = 0, zeros = 0;
+#pragma unroll
+                for (int x = 0; x < 5; ++x) { ones += (v[c][x] == 1.0f); zeros += (v[c][x] == 0.0f); }
+                oneHot = oneHot && (ones == 1) && (zeros == 4) && (v[c][5] == 0.0f);
+                // calculatePSGP, helper.cpp:185-196 (the ratio is evaluated in double, as upstream)
+                const float gg = v[c][P - 1];
+                float gOp = gapOpen, gEx = gapExtend;
+                if (gg > 0) {
+                    const double keep = static_cast<double>(__fsub_rn(numF, gg)) * 1.0 / static_cast<double>(sd.alnNum);
+                    gOp = fminf(minOpen, static_cast<float>(static_cast<double>(openScaled) * keep));
+                    gEx = fminf(minExtend, static_cast<float>(static_cast<double>(gapExtend) * keep));
+                }
+                const long long at = ntColIndex(idx, n4);
+                outX[at] = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
+                outY[at] = make_float4(v[c][4], v[c][5], gOp, gEx);
+                ++idx;
+            } else {
+                const bool pg = c ? gp[c - 1] : prevG;
+                const bool ng = (c + 1 < C) ? ((c + 1 < nHere) ? gp[c + 1] : false) : nextG;
+                if (!pg) { r[2 * runIdx] = t; ++runIdx; }
+                if (!ng) r[2 * (runIdx - 1) + 1] = t;                       // run end; turned into a length below
+            }
+        }
+        keptBase += chunkKept;
+        runBase += chunkStarts;
+    }
+    const int allOneHot = __syncthreads_and(oneHot ? 1 : 0);
+    for (int q = threadIdx.x; q < runBase; q += kLvlThreads) {
+        int *rr = r + 2 * q;
+        rr[1] = rr[1] - rr[0] + 1;
+    }
+    if (threadIdx.x == 0) {
+        sdRef.newLen = newLen;
+        sdRef.nRuns = runBase;
+        DevPair &pr = pairs[sd.pairIdx];
+        if (sd.isQry) { pr.qryLen = newLen; pr.qryN4 = n4; }
+        else { pr.refLen = newLen; pr.refN4 = n4; }
+        if (allOneHot && newLen > 0) atomicOr(&pr.pad, sd.isQry ? kQryOneHot : kRefOneHot);   // DP fast path, talco_wavefront.cu
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -535,15 +774,40 @@ __global__ void __launch_bounds__(kLvlThreads) rowUpdateKernel(const DevUpdate *
     }
     __syncthreads();
     const int nHere = min(kPathChunk, u.pathLen - k0);
-    // member rows (grid.z strides over them): ref members copy on 0/2, qry members on 0/1, '-' otherwise
-    for (int m = blockIdx.z; m < u.nRef + u.nQry; m += gridDim.z) {
-        const bool isRef = m < u.nRef;
-        const char *in = rowIn[u.memberOff + m];
-        char *out = rowOut[u.memberOff + m] + k0;
-        for (int e = threadIdx.x; e < nHere; e += kLvlThreads) {
-            const int op = ops[e];
-            const bool take = (op == 0) || (op == (isRef ? 2 : 1));
-            out[e] = take ? in[isRef ? srcR[e] : srcQ[e]] : '-';
+    // member rows (grid.z strides over them): ref members copy on 0/2, qry members on 0/1, '-' otherwise. A thread owns the four
+    // consecutive ops it scanned: the bytes it takes from a row are consecutive in the source (starting at its exclusive source
+    // index), so per row it reads the two aligned words that hold them (rows are 16-byte aligned and over-allocated), picks the
+    // bytes with one byte permutation whose selector depends on the ops only, and writes one aligned 32-bit word.
+    {
+        const int e0 = threadIdx.x * PER;
+        unsigned selR = 0, selQ = 0;          // per output byte: index 0..3 into the source window, or 4 = '-'
+        int pr = 0, pq = 0;
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+            const int op = ops[e0 + e];
+            const bool takeR = (op == 0 || op == 2), takeQ = (op == 0 || op == 1);
+            selR |= static_cast<unsigned>(takeR ? pr : 4) << (4 * e);
+            selQ |= static_cast<unsigned>(takeQ ? pq : 4) << (4 * e);
+            pr += takeR; pq += takeQ;
+        }
+        const int firstR = srcR[e0], firstQ = srcQ[e0];
+        const bool whole = e0 + PER <= nHere;
+        for (int m = blockIdx.z; m < u.nRef + u.nQry; m += gridDim.z) {
+            const bool isRef = m < u.nRef;
+            const char *in = rowIn[u.memberOff + m];
+            char *out = rowOut[u.memberOff + m] + k0;
+            const int first = isRef ? firstR : firstQ;
+            if (whole) {
+                const unsigned *w = reinterpret_cast<const unsigned *>(in) + (first >> 2);
+                const unsigned window = __funnelshift_r(w[0], w[1], 8 * (first & 3));
+                *reinterpret_cast<unsigned *>(out + e0) = __byte_perm(window, 0x2D2D2D2Du, isRef ? selR : selQ);
+            } else {
+                for (int e = e0; e < nHere; ++e) {
+                    const int op = ops[e];
+                    const bool take = (op == 0) || (op == (isRef ? 2 : 1));
+                    out[e] = take ? in[isRef ? srcR[e] : srcQ[e]] : '-';
+                }
+            }
         }
     }
     if (u.mergedOff >= 0 && blockIdx.z == 0) {                              // updateFrequency, helper.cpp:513-531

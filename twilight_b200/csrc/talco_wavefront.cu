@@ -31,7 +31,9 @@ namespace twl {
 
 
 struct WaveShared {
-    int4 red[2][32];            // per warp: (max score as ordered int, first live row, last live row, -)
+    alignas(16) int redMax[2][32];   // per warp: max score as ordered int ...
+    alignas(16) int redLo[2][32];    // ... first live row ...
+    alignas(16) int redHi[2][32];    // ... last live row (separate words: no packing moves, one 128-bit load fetches four warps)
     float2 edge[2][32];         // per warp: H and I of the warp's last slot (row-neighbour of the next warp's first slot)
     unsigned convMask[3];
     int8_t ops[2 * kMaxMarker + 16];
@@ -134,13 +136,13 @@ __global__ void __launch_bounds__(NT, (NT == 96 ? 6 : (NT <= 128 ? 640 / NT : (N
                         const int w = atomicAdd(a.queue, 1);
                         if (w < nMain) { got = a.order[w]; break; }
                     }
-                    // Watchdog: the producers bump the heartbeat every tile (a few ms at most). No beat for 50 ms means the narrow
+                    // Watchdog: the producers bump the heartbeat every tile (a few ms at most). No beat for 20 ms means the narrow
                     // kernel is not running next to us (profiler replay, CUDA_LAUNCH_BLOCKING): leave; whatever is handed over later
                     // is picked up by the clean-up launch that follows both kernels.
                     const int beat = *reinterpret_cast<volatile int *>(a.heartbeat) + *reinterpret_cast<volatile int *>(a.mainDone);
                     const unsigned long long now = globalTimerNs();
                     if (beat != lastBeat) { lastBeat = beat; lastChange = now; }
-                    else if (now - lastChange > 50000000ull) break;
+                    else if (now - lastChange > 20000000ull) { if (a.watchdog) atomicExch(a.watchdog, 1); break; }
                     __nanosleep(256);
                 }
                 sh.work = got; sh.fed = fed;
@@ -230,27 +232,29 @@ __global__ void __launch_bounds__(NT, (NT == 96 ? 6 : (NT <= 128 ? 640 / NT : (N
             const int prevWarp = (warp + NW - 1) % NW;
             int g0 = 1;
             float2 *const edgeOut = &sh.edge[0][warp];
-            int4 *const redOut = &sh.red[0][warp];
 
+            int c0 = 2;                                                // k % 3, kept incrementally
             for (int k = 0; k < nDiag; ++k) {
                 g0 ^= 1;
+                c0 = (c0 == 2) ? 0 : c0 + 1;
                 const int g1 = g0 ^ 1;
                 const int width = U0 - L0 + 1;
                 const int Lb = L0 & ~(kSlots - 1);                     // window base: multiple of 4 so a thread's rows never wrap
-                if (width <= 0 || width > cap || U0 - Lb >= W) {       // :323-338, plus this kernel's own capacity
+                if (static_cast<unsigned>(width - 1) >= static_cast<unsigned>(cap) || U0 - Lb >= W) {   // :323-338 (width <= 0 or > cap), plus this kernel's own capacity
                     error = (width <= 0) ? 1 : ((width > cap) ? 2 : kStatusRetryWide);
                     break;
                 }
                 tileCells += static_cast<unsigned>(width);
                 const float pruneBelow = __fsub_rn(maxScore, xdropF);
 
-                if (tid == 0) {   // warm L1 for the lines the band edges will touch a few diagonals from now
-                    // (one 128 B line holds 8 consecutive columns of one stream = a span of 32 columns, so each line is
-                    // touched on four consecutive diagonals; the four streams advance in turn)
-                    const long long jr = ntColIndex(refOff + min(refLen - 1, k - L0 + 40), pr.refN4);
-                    const long long iq = ntColIndex(qryOff + min(qryLen - 1, Lb + W + 40 + (k & 3)), pr.qryN4);
-                    prefetchL1(refX + jr); prefetchL1(refY + jr);
-                    prefetchL1(qryX + iq); prefetchL1(qryY + iq);
+                if ((k & 3) == 0 && warp == 0) {
+                    // Warm L1 for the lines the band edges will touch a few diagonals from now: one 128 B line holds 8 consecutive
+                    // float4 of one stream = a span of 32 columns, and the leading edge moves one column per diagonal, so every
+                    // fourth diagonal the 8 streams of each side are touched once (lanes 0-7 reference columns, 8-15 query rows).
+                    const int j = (lane < 8) ? refOff + min(refLen - 1, k - L0 + 43) : qryOff + min(qryLen - 1, Lb + W + 43);
+                    const int n4 = (lane < 8) ? pr.refN4 : pr.qryN4;
+                    const float4 *base = (lane < 8) ? refX : qryX;
+                    if (lane < 16) prefetchL1(base + static_cast<long long>(lane & 7) * n4 + (j >> 2));
                 }
 
                 // row-neighbour of slot 0: last slot of the previous thread (previous warp through shared memory)
@@ -455,9 +459,8 @@ __global__ void __launch_bounds__(NT, (NT == 96 ? 6 : (NT <= 128 ? 640 / NT : (N
                 int cs[kSlots], ci[kSlots], cd[kSlots];
 #pragma unroll
                 for (int c = 0; c < kSlots; ++c) cs[c] = ci[c] = cd[c] = 0;
-                const int c0 = k % 3;
                 if (k >= marker - 1 && __any_sync(0xffffffffu, actBits != 0)) {   // convergence pointers, reference indexing (:520-547)
-                    const int c1 = (c0 + 2) % 3, c2 = (c0 + 1) % 3;
+                    const int c1 = (c0 == 0) ? 2 : c0 - 1, c2 = (c0 == 2) ? 0 : c0 + 1;
                     if (k <= marker) {
 #pragma unroll
                         for (int c = 0; c < kSlots; ++c) {
@@ -498,27 +501,32 @@ __global__ void __launch_bounds__(NT, (NT == 96 ? 6 : (NT <= 128 ? 640 / NT : (N
                 const int wLo = __reduce_min_sync(0xffffffffu, myLo);
                 const int wHi = __reduce_max_sync(0xffffffffu, myHi);
                 if (lane == 31) edgeOut[g0 * 32] = make_float2(h1[kSlots - 1], i1[kSlots - 1]);
-                if (lane == 0) redOut[g0 * 32] = make_int4(wMax, wLo, wHi, 0);
+                if (lane == 0) { sh.redMax[g0][warp] = wMax; sh.redLo[g0][warp] = wLo; sh.redHi[g0][warp] = wHi; }
                 __syncthreads();
                 int oMax, newL, newU;
                 if (NW > 8) {           // many warps: one shared-memory read per lane and three warp reductions
-                    const int4 t = sh.red[g0][lane & (NW - 1)];
-                    oMax = __reduce_max_sync(0xffffffffu, t.x);
-                    newL = __reduce_min_sync(0xffffffffu, t.y);
-                    newU = __reduce_max_sync(0xffffffffu, t.z);
+                    oMax = __reduce_max_sync(0xffffffffu, sh.redMax[g0][lane & (NW - 1)]);
+                    newL = __reduce_min_sync(0xffffffffu, sh.redLo[g0][lane & (NW - 1)]);
+                    newU = __reduce_max_sync(0xffffffffu, sh.redHi[g0][lane & (NW - 1)]);
+                } else if (NW == 4) {   // four warps: one 128-bit load per quantity
+                    const int4 m = *reinterpret_cast<const int4 *>(&sh.redMax[g0][0]);
+                    const int4 lo = *reinterpret_cast<const int4 *>(&sh.redLo[g0][0]);
+                    const int4 hi = *reinterpret_cast<const int4 *>(&sh.redHi[g0][0]);
+                    oMax = max(max(m.x, m.y), max(m.z, m.w));
+                    newL = min(min(lo.x, lo.y), min(lo.z, lo.w));
+                    newU = max(max(hi.x, hi.y), max(hi.z, hi.w));
                 } else {
-                    oMax = sh.red[g0][0].x; newL = sh.red[g0][0].y; newU = sh.red[g0][0].z;
+                    oMax = sh.redMax[g0][0]; newL = sh.redLo[g0][0]; newU = sh.redHi[g0][0];
 #pragma unroll
                     for (int w = 1; w < NW; ++w) {
-                        const int4 t = sh.red[g0][w];
-                        oMax = max(oMax, t.x); newL = min(newL, t.y); newU = max(newU, t.z);
+                        oMax = max(oMax, sh.redMax[g0][w]); newL = min(newL, sh.redLo[g0][w]); newU = max(newU, sh.redHi[g0][w]);
                     }
                 }
                 if (newL == 0x7fffffff) { newL = U0 + 1; newU = L0 - 1; }
                 maxScorePrime = fmaxf(maxScorePrime, orderedFloat(oMax));
 
                 if (!converged && k >= marker && k < nDiag - 1) {       // :585-595
-                    const int c2 = (c0 + 1) % 3;
+                    const int c2 = (c0 == 2) ? 0 : c0 + 1;
                     const int start = newL - L0;
                     const int vI = sCI[g0][start], vD = sCD[g0][start], vS = sCS[c0][start];
                     unsigned bad = 0;
@@ -546,7 +554,7 @@ __global__ void __launch_bounds__(NT, (NT == 96 ? 6 : (NT <= 128 ? 640 / NT : (N
                 L2 = L1; U2 = U1; L1 = L0; U1 = U0;
                 L0 = max(newL, max(0, k + 2 - refLen));
                 U0 = min(qryLen - 1, newU + 1);
-                maxScore = (maxScorePrime < 0.0f) ? 0.0f : maxScorePrime;
+                maxScore = fmaxf(maxScorePrime, 0.0f);                   // max(0, max_score_prime), :607 (a -0 maximum compares and subtracts like +0)
                 lastK = k;
                 if (converged && maxScore > convScore) { stopped = true; break; }
             }

@@ -137,7 +137,7 @@ void twl_destroy(twl_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     ctx->dScore.release(); ctx->dProf.release(); ctx->dPairs.release(); ctx->dResults.release(); ctx->dPaths.release();
     ctx->dOrder.release(); ctx->dOverflow.release(); ctx->dCounters.release(); ctx->dTb.release(); ctx->dState.release();
-    ctx->hProf.release(); ctx->hPaths.release(); ctx->hResults.release();
+    ctx->hProf.release(); ctx->hPaths.release(); ctx->hResults.release(); ctx->hWatchdog.release();
     if (ctx->evStart) cudaEventDestroy(ctx->evStart);
     if (ctx->evStop) cudaEventDestroy(ctx->evStop);
     if (ctx->evFork) cudaEventDestroy(ctx->evFork);
@@ -263,6 +263,7 @@ int twl_batch_stage(twl_ctx *ctx, const twl_profile_pair *pairs, int n_pairs) {
 //   protein   : generic/shared state (band <= 1020)                            -> generic/global state
 int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
     const int marker = ctx->marker;
+    if (ctx->hWatchdog.ptr && *ctx->hWatchdog.ptr && ctx->wideWorkers > 0) ctx->wideWorkers = 0;   // an earlier chain's wide workers timed out: stop co-running
     const int wideCap = std::max(wideCapIn, 8);                     // widest band any pair of the batch may legally reach
     const bool nucleotide = (ctx->P == 6) && !ctx->forceGeneric;
     struct Stage { int kind; int threads; int cap; int grid; size_t tbStride; int slots; };   // kind 0 wavefront (CTA per pair), 1 generic smem, 2 generic global, 3 warp per pair
@@ -377,6 +378,7 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
             w.resume = 0;
             w.mainDone = ctx->dCounters.ptr + 14;
             w.heartbeat = ctx->dCounters.ptr + 15;
+            w.watchdog = ctx->dCounters.ptr + 13;
             w.feedList = ctx->dOverflow.ptr;
             w.feedCount = ctx->dCounters.ptr + 3;
             w.feedCursor = ctx->dCounters.ptr + 2;
@@ -429,6 +431,9 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
                 TWL_CUDA(ctx, twl::launchTalcoWavefront(sw.threads, sw.slots, matClass, c, std::min(n, ctx->smCount), ctx->stream));
                 ctx->lastLaunches += 1;
             }
+            // did a wide worker give up waiting? read at the next chain (pinned copy, in stream order after the kernels)
+            if (!ctx->hWatchdog.ptr) { TWL_CUDA(ctx, ctx->hWatchdog.reserve(1)); *ctx->hWatchdog.ptr = 0; }
+            TWL_CUDA(ctx, cudaMemcpyAsync(ctx->hWatchdog.ptr, ctx->dCounters.ptr + 13, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
             ++s;   // stage 1 ran alongside
             continue;
         }

@@ -83,6 +83,9 @@ struct twl_ctx {
     int dpTrace = 0;
     int maxCtasPerSm = 0;        // cap on resident CTAs per SM of the wavefront stages (0 = as many as fit); occupancy experiments
     int wideWorkers = 8;         // CTAs of the wide wavefront kernel that run next to the narrow one (0 = run the wide stage afterwards)
+    PinBuf<int> hWatchdog;       // copy of the device flag a wide worker sets when its 20 ms watchdog fires: the two kernels were not
+                                 // co-scheduled (MPS / time slicing, profiler, CUDA_LAUNCH_BLOCKING) -> co-running is switched off for
+                                 // the rest of the context's life instead of paying the watchdog at every level
     cudaStream_t stream2 = nullptr;
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
     int wideThreads = 512;       // second wavefront stage (1024-row window): 512 threads x 2 rows, or 256 x 4

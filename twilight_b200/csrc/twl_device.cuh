@@ -82,6 +82,7 @@ struct TalcoArgs {
     int coTakeBelow;         // mode 2: also take main-queue entries with index below this (0 = never). Large batches only, and not
                              // the last wave, so that pairs handed over near the end find an idle wide worker
     int *mainDone;           // pairs of the main queue that are completely finished (either kernel)
+    int *watchdog;           // set by a wide worker that gave up waiting (kernels were not co-scheduled): the host then stops co-running
     int *heartbeat;          // bumped by the narrow kernel at every tile: lets a waiting wide worker tell "still running" from
                              // "not running at all" (kernels serialised by a profiler or CUDA_LAUNCH_BLOCKING)
     int *feedList;           // mode 2: entries appended by the producers (-1 until written)

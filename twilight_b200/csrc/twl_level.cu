@@ -46,6 +46,7 @@ struct TwlLevelState {
     DevBuf<char *> dRowOut;
     DevBuf<float> dRowW, dRaw, dFreq, dMerged;
     DevBuf<char> dCons;
+    DevBuf<float> dGap;
     DevBuf<int> dRuns, dChunkCounts;
     DevBuf<twl::DevUpdate> dUps;
     DevBuf<int8_t> dFinalPaths;
@@ -69,8 +70,9 @@ struct TwlLevelState {
     cudaEvent_t stageFree = nullptr;      // recorded after the last asynchronous use of hStage / dStage / dCopies
     bool stagePending = false;
     std::vector<cudaEvent_t> sliceEv;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     float phaseMs[4] = {0, 0, 0, 0};
+    float restoreMs = 0.f;       // the gappy-column restore share of phaseMs[3]
 
     std::vector<PairKeep> keep;
     int lastChunks = 0;
@@ -136,7 +138,7 @@ size_t rowSizeClass(size_t bytes) {
 }
 
 cudaError_t poolAlloc(TwlLevelState *L, size_t bytes, char **out) {
-    bytes = rowSizeClass(bytes);
+    bytes = rowSizeClass(bytes + 16);   // 16 bytes of slack: the level kernels read rows in aligned 32-bit words, up to 7 bytes past the text
     auto it = L->freeBufs.find(bytes);
     if (it != L->freeBufs.end() && !it->second.empty()) {
         *out = it->second.back();
@@ -167,7 +169,7 @@ cudaError_t poolAlloc(TwlLevelState *L, size_t bytes, char **out) {
 }
 
 void poolRecycle(TwlLevelState *L, char *buf, size_t cap) {
-    if (buf) L->freeBufs[rowSizeClass(cap)].push_back(buf);
+    if (buf) L->freeBufs[rowSizeClass(cap + 16)].push_back(buf);
 }
 
 // letterIdx (src/scoring-matrix.cpp:26-79) on the host: only used to build the 256-entry protein lookup table the kernels read
@@ -198,7 +200,7 @@ void twlLevelDestroy(twl_ctx *ctx) {
     if (!L) return;
     for (void *p : L->pools) cudaFree(p);
     L->dSides.release(); L->dRowIn.release(); L->dRowOut.release(); L->dRowW.release(); L->dRaw.release(); L->dFreq.release();
-    L->dMerged.release(); L->dCons.release(); L->dRuns.release(); L->dChunkCounts.release(); L->dUps.release();
+    L->dMerged.release(); L->dCons.release(); L->dGap.release(); L->dRuns.release(); L->dChunkCounts.release(); L->dUps.release();
     L->dFinalPaths.release(); L->dAaLut.release(); L->dCopies.release(); L->dStage.release(); L->hStage.release();
     L->hRes.release(); L->hUps.release(); L->hNeed.release(); L->hFinal.release(); L->hSides.release(); L->hFreqPin.release(); L->hMergedPin.release();
     L->dUps2.release(); L->dUpdPair.release(); L->dNeed.release(); L->dWhich.release(); L->dLargeScratch.release(); L->dUpdIn.release();
@@ -464,6 +466,13 @@ int twl_rows_download(twl_ctx *ctx, int n, const int32_t *ids, char *const *dst,
     return TWL_OK;
 }
 
+int twl_level_update_split_ms(twl_ctx *ctx, float out[2]) {
+    if (!ctx || !out) return TWL_E_ARG;
+    out[0] = ctx->level ? ctx->level->restoreMs : 0.f;
+    out[1] = ctx->level ? ctx->level->phaseMs[3] - ctx->level->restoreMs : 0.f;
+    return TWL_OK;
+}
+
 int twl_level_phase_ms(twl_ctx *ctx, float out[4]) {
     if (!ctx || !out) return TWL_E_ARG;
     for (int i = 0; i < 4; ++i) out[i] = ctx->level ? ctx->level->phaseMs[i] : 0.f;
@@ -534,7 +543,7 @@ int runLevelChunkImpl(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pair
                 rowIn.push_back(r.buf[r.storage]);
                 rowW.push_back(r.weight);
             }
-            d.rawOff = static_cast<long long>(rawWords); rawWords += static_cast<size_t>(nd.aln_len) * P;
+            d.rawOff = static_cast<long long>(rawWords); rawWords += (static_cast<size_t>(nd.aln_len) * P + 3) & ~static_cast<size_t>(3);   // 16-byte aligned sides
             d.consOff = static_cast<long long>(consBytes); consBytes += (static_cast<size_t>(nd.aln_len) + 15) & ~static_cast<size_t>(15);
             d.runsOff = static_cast<long long>(runInts); runInts += 2 * (static_cast<size_t>(nd.aln_len) / 2 + 2);
             d.profOff = static_cast<long long>(profWords); profWords += sideWordsL(nd.aln_len, P);
@@ -572,6 +581,7 @@ int runLevelChunkImpl(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pair
     TWL_CUDA(ctx, L->dRowW.reserve(std::max<size_t>(rowW.size(), 1)));
     TWL_CUDA(ctx, L->dRaw.reserve(std::max<size_t>(rawWords, 1)));
     TWL_CUDA(ctx, L->dCons.reserve(std::max<size_t>(consBytes, 16)));
+    if (P == 6) TWL_CUDA(ctx, L->dGap.reserve(std::max<size_t>(consBytes, 16)));   // per-column gap counts (floats, laid out like the consensus)
     TWL_CUDA(ctx, L->dRuns.reserve(std::max<size_t>(runInts, 2)));
     TWL_CUDA(ctx, L->dFreq.reserve(std::max<size_t>(freqWords, 1)));
     {
@@ -700,16 +710,25 @@ int runLevelChunkImpl(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pair
     tr.mark("reserve + H2D description");
     // ---- phase 1: profiles + consensus (+ msaFreq cache); phase 2: gappy-column compaction + PSGP + DP packing
     TWL_CUDA(ctx, cudaEventRecord(L->ev[0], ctx->stream));
-    {
+    if (P == 6) {
+        dim3 grid(nSides, std::max(1, (maxLen + kProfThreads * kProfCols - 1) / (kProfThreads * kProfCols)));
+        profileBuildNtKernel<<<grid, kProfThreads, 0, ctx->stream>>>(L->dSides.ptr, L->dRowIn.ptr, L->dRowW.ptr, L->dRaw.ptr, L->dCons.ptr,
+                                                                    L->dFreq.ptr, L->dFreq.ptr, L->dGap.ptr);
+        TWL_CUDA(ctx, cudaGetLastError());
+        TWL_CUDA(ctx, cudaEventRecord(L->ev[1], ctx->stream));
+        gappyCompactNtKernel<<<nSides, kLvlThreads, 0, ctx->stream>>>(L->dSides.ptr, L->dRaw.ptr, L->dGap.ptr, ctx->dProf.ptr + kProfPadWords, L->dRuns.ptr,
+                                                                     ctx->dPairs.ptr, threshold, ctx->gapOpen, ctx->gapExtend);
+        TWL_CUDA(ctx, cudaGetLastError());
+    } else {
         dim3 grid(nSides, std::max(1, (maxLen + kLvlThreads - 1) / kLvlThreads));
         profileBuildKernel<P><<<grid, kLvlThreads, 0, ctx->stream>>>(L->dSides.ptr, L->dRowIn.ptr, L->dRowW.ptr, L->dRaw.ptr, L->dCons.ptr,
                                                                  L->dFreq.ptr, L->dFreq.ptr, L->dAaLut.ptr);
         TWL_CUDA(ctx, cudaGetLastError());
+        TWL_CUDA(ctx, cudaEventRecord(L->ev[1], ctx->stream));
+        gappyCompactKernel<P><<<nSides, kLvlThreads, 0, ctx->stream>>>(L->dSides.ptr, L->dRaw.ptr, ctx->dProf.ptr + kProfPadWords, L->dRuns.ptr,
+                                                                       ctx->dPairs.ptr, threshold, ctx->gapOpen, ctx->gapExtend);
+        TWL_CUDA(ctx, cudaGetLastError());
     }
-    TWL_CUDA(ctx, cudaEventRecord(L->ev[1], ctx->stream));
-    gappyCompactKernel<P><<<nSides, kLvlThreads, 0, ctx->stream>>>(L->dSides.ptr, L->dRaw.ptr, ctx->dProf.ptr + kProfPadWords, L->dRuns.ptr,
-                                                                   ctx->dPairs.ptr, threshold, ctx->gapOpen, ctx->gapExtend);
-    TWL_CUDA(ctx, cudaGetLastError());
     TWL_CUDA(ctx, cudaEventRecord(L->ev[2], ctx->stream));
     ctx->lastLaunches += 2;
 
@@ -763,6 +782,7 @@ int runLevelChunkImpl(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pair
             L->dFinalPaths.ptr, ctx->dScore.ptr, ctx->M, P == 6 ? 0 : 1, L->dAaLut.ptr, ctx->gapOpen, ctx->gapExtend, L->dNeed.ptr, nullptr, 0, 0);
         TWL_CUDA(ctx, cudaGetLastError());
         ctx->lastLaunches += 1;
+        TWL_CUDA(ctx, cudaEventRecord(L->ev[6], ctx->stream));
         const int rc = launchUpdate(L->dUps.ptr, nu, maxUb, maxRows);
         if (rc != TWL_OK) return rc;
     }
@@ -885,6 +905,8 @@ int runLevelChunkImpl(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pair
         float ms = 0.f;
         cudaEventElapsedTime(&ms, L->ev[5], L->ev[4]);
         L->phaseMs[3] += ms;
+        cudaEventElapsedTime(&ms, L->ev[5], L->ev[6]);
+        L->restoreMs += ms;
     }
     return TWL_OK;
 }
@@ -912,6 +934,7 @@ int twl_align_level(twl_ctx *ctx, const twl_level_pair *pairs, int n_pairs, int 
     L->keep.assign(n_pairs, PairKeep());
     L->P = ctx->P;
     for (float &m : L->phaseMs) m = 0.f;
+    L->restoreMs = 0.f;
     if (cache_threshold <= 0) cache_threshold = 1000;
     // chunk the level so that the scratch (raw profiles dominate: 4*P bytes per column and side) stays bounded
     size_t budget = static_cast<size_t>(12) << 30;

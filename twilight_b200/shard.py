@@ -37,13 +37,14 @@ def subtree_affinity(levels, world: int, n_nodes: int) -> np.ndarray:
             children[parent] = (a, b)
     root = levels[-1][0][2]
 
-    def count(v):
-        if v not in children:
-            size[v] = 1
-        else:
-            size[v] = count(children[v][0]) + count(children[v][1])
-        return size[v]
-    count(root)
+    # leaf counts bottom-up: levels are already in dependency order (children before parents), so no recursion is needed
+    # (a caterpillar-shaped guide tree is thousands of nodes deep)
+    for level in levels:
+        for a, b, parent in level:
+            for c in (a, b):
+                if size[c] == 0:
+                    size[c] = 1
+            size[parent] = size[a] + size[b]
     # split the tree top-down into `world` subtrees of roughly equal leaf count
     parts = [root]
     while len(parts) < world:
@@ -54,14 +55,13 @@ def subtree_affinity(levels, world: int, n_nodes: int) -> np.ndarray:
         parts.extend(children[big])
     bins = lpt_partition([float(size[p]) for p in parts], world)
 
-    def paint(v, r):
-        owner[v] = r
-        if v in children:
-            paint(children[v][0], r)
-            paint(children[v][1], r)
     for r, items in enumerate(bins):
-        for k in items:
-            paint(parts[k], r)
+        stack = [parts[k] for k in items]
+        while stack:                                   # explicit stack: depth is unbounded for unbalanced trees
+            v = stack.pop()
+            owner[v] = r
+            if v in children:
+                stack.extend(children[v])
     # ancestors of the split points: owned by the rank of their first child (rows migrate once, at the top of the tree)
     for level in levels:
         for a, b, parent in level:
