@@ -85,6 +85,7 @@ constexpr size_t kPoolChunkBytes = static_cast<size_t>(256) << 20;
 
 TwlLevelState *levelOf(twl_ctx *ctx) {
     if (!ctx->level) {
+        cudaSetDevice(ctx->device);           // the events below belong to the context's device, whatever device the caller had current
         ctx->level = new TwlLevelState();
         for (auto &e : ctx->level->ev) cudaEventCreate(&e);
         cudaEventCreateWithFlags(&ctx->level->stageFree, cudaEventDisableTiming);
