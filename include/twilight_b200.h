@@ -189,13 +189,12 @@ int twl_level_large_restores(const twl_ctx *ctx);
 float twl_last_kernel_ms(const twl_ctx *ctx);
 int twl_last_launch_count(const twl_ctx *ctx);
 
-/* Tuning / diagnostics switches. "force_generic" = 1 routes nucleotide batches through the wide-band generic kernel
- * instead of the register-resident wavefront kernel (results are identical; used by the A/B parity tests).
- * "dp_kernel" = 1 (default) one pair per CTA, register-resident wavefront; 2 = experimental one pair per warp
- * (talco_warp.cu; same results, currently slower); 0 = choose by batch size. "warp_ctas_per_sm", "warp_min_pairs" tune 2/0.
- * "wide_workers" (default 8; 0 = run the wide-band kernel after the narrow one instead of beside it), "wide_threads"
- * (512 or 256), "first_threads" (128 or 96), "latency_mode" (-1 auto, 0 off, 1 always) and "latency_shape" (0..3) select
- * among bit-identical schedules / instantiations of the wavefront kernel; "dp_trace" = 1 prints per-stage times to stderr.
+/* Tuning / diagnostics switches; every setting produces identical results. "force_generic" = 1 routes nucleotide batches
+ * through the wide-band generic kernel instead of the register-resident wavefront kernel (A/B parity tests). "wide_workers"
+ * (default 8; 0 = run the wide-band kernel after the narrow one instead of beside it), "latency_mode" (-1 auto, 0 off,
+ * 1 always: the one-CTA-per-SM shape for levels with few pairs), "latency_shape" (2 = 512 threads x 2 rows, default;
+ * 3 = 512 x 1 first and 512 x 2 for pairs whose band outgrows 512 rows), "max_ctas_per_sm" (occupancy experiments),
+ * "dp_trace" = 1 prints per-stage times to stderr.
  * The environment variable TWL_OPTIONS="name=value,name=value" applies the same switches at twl_init. */
 int twl_set_option(twl_ctx *ctx, const char *name, int value);
 

@@ -16,6 +16,7 @@ SCENARIOS = {
     "rna_3k_default": ("rna_3k", []),                 # nodes >= 1000 sequences: msaFreq caching + parking (helper.cpp:14,35-40,479-500)
     "rna_3k_m1000": ("rna_3k", ["-m", "1000"]),
     "rna_10k_default": ("rna_10k", []),
+    "rna_100k_default": ("rna_100k", []),             # bench.py's C3 rung; not part of the pytest parametrisation (see test_cli_synth_gpu.py)
     "sars_64_default": ("sars_64", []),
     "sars_64_m20": ("sars_64", ["-m", "20"]),
     "prot_2k_default": ("prot_2k", ["--type", "p"]),

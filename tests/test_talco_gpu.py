@@ -175,25 +175,11 @@ def test_unstructured_matrix_path(which):
         assert np.array_equal(o.path, r.aln_wo), f"pair {k}"
 
 
-def test_warp_per_pair_kernel_matches_port():
-    """The experimental one-pair-per-warp kernel (twl_set_option dp_kernel=2) must produce the same bits."""
-    import twilight_b200
-    cfg, _, _, _, recs = synthetic_records(12, 900, 23, 128)
-    ctx = twilight_b200.Context(marker=128)
-    ctx.set_option("dp_kernel", 2)
-    outs = ctx.align_profiles(records_to_pairs(recs, cfg))
-    ctx.close()
-    for k, (o, r) in enumerate(zip(outs, recs)):
-        assert o.status == r.error == 0
-        assert o.cells == r.cells and o.tiles == r.tiles
-        assert np.array_equal(o.path, r.aln_wo), f"pair {k}"
-
-
-@pytest.mark.parametrize("shape", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("shape", [2, 3])
 @pytest.mark.parametrize("n,L,seed,marker", [(12, 900, 29, 128), (6, 2500, 31, 1024)])
 def test_low_latency_variant_matches_port(n, L, seed, marker, shape):
-    """The instantiations used for levels with few pairs (twl_set_option latency_mode=1): 256 threads x 2 rows (shape 0)
-    and 512 threads x 1 row (shape 1)."""
+    """The instantiations used for levels with few pairs (twl_set_option latency_mode=1): 512 threads x 2 rows (shape 2) and
+    512 x 1 followed by 512 x 2 (shape 3)."""
     import twilight_b200
     cfg, _, _, _, recs = synthetic_records(n, L, seed, marker)
     ctx = twilight_b200.Context(marker=marker)
@@ -207,7 +193,7 @@ def test_low_latency_variant_matches_port(n, L, seed, marker, shape):
         assert np.array_equal(o.path, r.aln_wo), f"pair {k}"
 
 
-@pytest.mark.parametrize("shape", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("shape", [2, 3])
 def test_low_latency_variant_overflows_to_wide(shape):
     """Bands wider than the 512-row window of the low-latency variant continue in the 1024-row kernel (and beyond),
     same bits as the oracle."""
@@ -218,40 +204,6 @@ def test_low_latency_variant_overflows_to_wide(shape):
     ctx.set_option("latency_mode", 1)
     ctx.set_option("latency_shape", shape)
     for xdrop in (5000, 9000, 14000, 40000):
-        c = ol.TalcoCfg(xdrop=xdrop)
-        want, err, cells, tiles, _ = ol.port_talco(c, r.profile[0], r.profile[1], r.gap_op[0], r.gap_ex[0], r.gap_op[1], r.gap_ex[1], 1, 1)
-        pair = twilight_b200.ProfilePairIn(r.profile[0], r.profile[1], r.gap_op[0], r.gap_ex[0], r.gap_op[1], r.gap_ex[1], 1, 1, xdrop=xdrop)
-        out = ctx.align_profiles([pair])[0]
-        assert out.status == err == 0, xdrop
-        assert out.cells == cells, xdrop
-        assert np.array_equal(out.path, want), xdrop
-    ctx.close()
-
-
-@pytest.mark.parametrize("n,L,seed,marker", [(12, 900, 37, 128), (6, 2500, 41, 1024)])
-def test_narrow_window_variant_matches_port(n, L, seed, marker):
-    """96 threads x 4 rows: a 384-row window (not a power of two) as the first stage (twl_set_option first_threads=96)."""
-    import twilight_b200
-    cfg, _, _, _, recs = synthetic_records(n, L, seed, marker)
-    ctx = twilight_b200.Context(marker=marker)
-    ctx.set_option("first_threads", 96)
-    ctx.set_option("latency_mode", 0)
-    outs = ctx.align_profiles(records_to_pairs(recs, cfg))
-    ctx.close()
-    for k, (o, r) in enumerate(zip(outs, recs)):
-        assert o.status == r.error == 0
-        assert o.cells == r.cells and o.tiles == r.tiles
-        assert np.array_equal(o.path, r.aln_wo), f"pair {k}"
-
-
-def test_narrow_window_variant_overflows_to_wide():
-    import twilight_b200
-    cfg, _, _, _, recs = synthetic_records(2, 2400, 19, 1024)
-    r = recs[0]
-    ctx = twilight_b200.Context(marker=1024)
-    ctx.set_option("first_threads", 96)
-    ctx.set_option("latency_mode", 0)
-    for xdrop in (5000, 7000, 9000, 14000, 40000):
         c = ol.TalcoCfg(xdrop=xdrop)
         want, err, cells, tiles, _ = ol.port_talco(c, r.profile[0], r.profile[1], r.gap_op[0], r.gap_ex[0], r.gap_op[1], r.gap_ex[1], 1, 1)
         pair = twilight_b200.ProfilePairIn(r.profile[0], r.profile[1], r.gap_op[0], r.gap_ex[0], r.gap_op[1], r.gap_ex[1], 1, 1, xdrop=xdrop)

@@ -39,6 +39,17 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed building libtwilight_b200.so")
     if verbose:
         sys.stderr.write(res.stderr)
+    # build stamp: which sources (sha1), which compiler, when — so a "does it build" check leaves evidence that it compiled
+    import hashlib
+    import json
+    import time
+    h = hashlib.sha1()
+    for path in sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + sorted(glob.glob(os.path.join(CSRC, "*.hpp"))):
+        h.update(open(path, "rb").read())
+    ver = subprocess.run([nvcc, "--version"], capture_output=True, text=True).stdout.strip().splitlines()[-1:]
+    with open(os.path.join(PKG, "BUILD_INFO.json"), "w") as f:
+        json.dump({"library": os.path.basename(LIB), "built_at": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime()), "nvcc": ver, "flags": NVCC_FLAGS,
+                   "sources": [os.path.basename(p) for p in sources()], "sources_sha1": h.hexdigest(), "bytes": os.path.getsize(LIB)}, f, indent=1)
     return LIB
 
 

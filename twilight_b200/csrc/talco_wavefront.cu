@@ -92,7 +92,7 @@ __device__ __forceinline__ void numerators4(const float (&r)[KS][6], const float
 // KS = rows per thread: 4 for throughput (W = 4*NT); 2 with NT = 256 for levels with few pairs, where a CTA runs alone on
 // its SM and the per-thread instruction stream, not the issue rate, sets the time of a diagonal.
 template <int NT, int MC, int KS>
-__global__ void __launch_bounds__(NT, (NT == 96 ? 6 : (NT <= 128 ? 640 / NT : (NT <= 256 ? 2 : 1)))) talcoWavefrontKernel(const TalcoArgs a) {
+__global__ void __launch_bounds__(NT, (NT <= 128 ? 640 / NT : 1)) talcoWavefrontKernel(const TalcoArgs a) {
     constexpr int kSlots = KS;
     constexpr int W = NT * kSlots;
     constexpr int NW = NT / 32;
@@ -695,16 +695,12 @@ cudaError_t launchDivSelfTest(const float *num, const float *den, int n, int *mi
     return cudaGetLastError();
 }
 
-// supported instantiations: (threads, slots) = (128,4) throughput, (256,4) wide band, (256,2) low latency
+// supported instantiations: (threads, slots) = (128,4) throughput, (512,2) wide band / low latency, (512,1) narrow-band low latency
 template <int MC>
 static cudaError_t launchMc(int threads, int slots, const TalcoArgs &args, int grid, cudaStream_t stream) {
     if (threads == 128 && slots == 4) talcoWavefrontKernel<128, MC, 4><<<grid, 128, 0, stream>>>(args);
-    else if (threads == 96 && slots == 4) talcoWavefrontKernel<96, MC, 4><<<grid, 96, 0, stream>>>(args);
-    else if (threads == 256 && slots == 4) talcoWavefrontKernel<256, MC, 4><<<grid, 256, 0, stream>>>(args);
-    else if (threads == 256 && slots == 2) talcoWavefrontKernel<256, MC, 2><<<grid, 256, 0, stream>>>(args);
     else if (threads == 512 && slots == 1) talcoWavefrontKernel<512, MC, 1><<<grid, 512, 0, stream>>>(args);
     else if (threads == 512 && slots == 2) talcoWavefrontKernel<512, MC, 2><<<grid, 512, 0, stream>>>(args);
-    else if (threads == 1024 && slots == 1) talcoWavefrontKernel<1024, MC, 1><<<grid, 1024, 0, stream>>>(args);
     else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
@@ -717,9 +713,9 @@ int wavefrontMaxCtasPerSm(int threads, int slots, int matClass) {
     int n = 0;
 #define TWL_OCC(NT_, MC_, KS_) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, talcoWavefrontKernel<NT_, MC_, KS_>, NT_, 0)
     if (matClass == 1) {
-        if (threads == 128 && slots == 4) TWL_OCC(128, 1, 4); else if (threads == 96 && slots == 4) TWL_OCC(96, 1, 4); else if (threads == 256 && slots == 4) TWL_OCC(256, 1, 4); else if (threads == 256 && slots == 2) TWL_OCC(256, 1, 2); else if (threads == 512 && slots == 1) TWL_OCC(512, 1, 1); else if (threads == 512 && slots == 2) TWL_OCC(512, 1, 2); else if (threads == 1024 && slots == 1) TWL_OCC(1024, 1, 1);
+        if (threads == 128 && slots == 4) TWL_OCC(128, 1, 4); else if (threads == 512 && slots == 1) TWL_OCC(512, 1, 1); else if (threads == 512 && slots == 2) TWL_OCC(512, 1, 2);
     } else {
-        if (threads == 128 && slots == 4) TWL_OCC(128, 0, 4); else if (threads == 96 && slots == 4) TWL_OCC(96, 0, 4); else if (threads == 256 && slots == 4) TWL_OCC(256, 0, 4); else if (threads == 256 && slots == 2) TWL_OCC(256, 0, 2); else if (threads == 512 && slots == 1) TWL_OCC(512, 0, 1); else if (threads == 512 && slots == 2) TWL_OCC(512, 0, 2); else if (threads == 1024 && slots == 1) TWL_OCC(1024, 0, 1);
+        if (threads == 128 && slots == 4) TWL_OCC(128, 0, 4); else if (threads == 512 && slots == 1) TWL_OCC(512, 0, 1); else if (threads == 512 && slots == 2) TWL_OCC(512, 0, 2);
     }
 #undef TWL_OCC
     return n;

@@ -21,10 +21,6 @@ int wavefrontWindow(int threads, int slots);
 int nucleotideMatrixClass(const float *score5x5);
 cudaError_t launchTalcoWavefront(int threads, int slots, int matClass, const TalcoArgs &args, int grid, cudaStream_t stream);
 int wavefrontMaxCtasPerSm(int threads, int slots, int matClass);
-int warpKernelBandCapacity();
-int warpKernelWindow();
-cudaError_t launchTalcoWarp(int matClass, const TalcoArgs &args, int grid, cudaStream_t stream);
-int warpKernelMaxCtasPerSm(int matClass);
 cudaError_t launchDivSelfTest(const float *num, const float *den, int n, int *mismatches, cudaStream_t stream);
 } // namespace twl
 
@@ -270,25 +266,18 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
     const int matClass = nucleotide ? twl::nucleotideMatrixClass(ctx->hScore.data()) : 0;
     std::vector<Stage> stages;
     auto tbRows = [&](int w) { return (static_cast<size_t>(marker + 1) * w + 255) & ~static_cast<size_t>(255); };
-    // many pairs: throughput kernel (one pair per warp) first; few pairs: the CTA-per-pair kernel has the lower latency
-    const bool useWarp = nucleotide && (ctx->dpKernel == 2 || (ctx->dpKernel == 0 && n >= ctx->warpMinPairs));
-    if (useWarp) {
-        const int perSm = std::max(1, std::min(ctx->warpCtasPerSm, twl::warpKernelMaxCtasPerSm(matClass)));
-        stages.push_back({3, 32, twl::warpKernelBandCapacity(), std::min(n, ctx->smCount * perSm), tbRows(twl::warpKernelWindow()), 0});
-    }
     if (nucleotide) {
-        // few pairs (every CTA has an SM to itself): 256 threads x 2 rows shortens the per-thread instruction stream of a
-        // diagonal, which is what bounds a lone CTA; otherwise 128 threads x 4 rows, 5 CTAs per SM
-        const bool lowLatency = !useWarp && ctx->latencyMode != 0 && (ctx->latencyMode == 1 || n <= ctx->smCount);
-        // latency shapes: 0 = 256x2 then 256x4, 1 = 512x1 then 256x4, 2 = 512x2 (1024-row window at once), 3 = 512x1 then 512x2,
-        // 4 = 1024x1 (1024-row window, one row per thread)
-        static const int shapes[5][2][2] = {{{256, 2}, {256, 4}}, {{512, 1}, {256, 4}}, {{512, 2}, {0, 0}}, {{512, 1}, {512, 2}}, {{1024, 1}, {0, 0}}};
-        const int sh = std::min(std::max(ctx->latencyShape, 0), 4);
-        int plan[4][2] = {{ctx->firstThreads, 4}, {ctx->wideThreads, ctx->wideThreads == 512 ? 2 : 4}, {0, 0}, {0, 0}};
-        if (lowLatency) { plan[0][0] = shapes[sh][0][0]; plan[0][1] = shapes[sh][0][1]; plan[1][0] = shapes[sh][1][0]; plan[1][1] = shapes[sh][1][1]; }
-        for (int s = 0; plan[s][0]; ++s) {
+        // few pairs (every CTA has an SM to itself): 512 threads x 2 rows, one 1024-row window for any legal nucleotide band
+        // (latency_shape 3: 512 x 1 first, 512 x 2 for pairs whose band outgrows 512 rows); otherwise 128 threads x 4 rows,
+        // 5 CTAs per SM, with 512 x 2 as the wide stage
+        const bool lowLatency = ctx->latencyMode != 0 && (ctx->latencyMode == 1 || n <= ctx->smCount);
+        int plan[3][2] = {{128, 4}, {512, 2}, {0, 0}};
+        if (lowLatency) {
+            if (ctx->latencyShape == 3) { plan[0][0] = 512; plan[0][1] = 1; }
+            else { plan[0][0] = 512; plan[0][1] = 2; plan[1][0] = 0; }
+        }
+        for (int s = 0; s < 3 && plan[s][0]; ++s) {
             const int threads = plan[s][0], slots = plan[s][1];
-            if (useWarp && s == 0) continue;
             const int cap = twl::wavefrontBandCapacity(threads, slots);
             int perSm = std::max(1, twl::wavefrontMaxCtasPerSm(threads, slots, matClass));
             if (ctx->maxCtasPerSm > 0) perSm = std::min(perSm, ctx->maxCtasPerSm);
@@ -302,7 +291,7 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
     if (wideCap > stages.back().cap) stages.push_back({2, twl::genericThreads(), wideCap, std::min(n, ctx->smCount), tbBytesPerCta(marker), 0});
 
     // Co-run: stage 0 (narrow window, 5 CTAs per SM) and stage 1 (wide window) execute at the same time; see TalcoArgs::coMode.
-    const bool coRun = nucleotide && !useWarp && ctx->wideWorkers > 0 && stages.size() >= 2 && stages[0].kind == 0 && stages[1].kind == 0 &&
+    const bool coRun = nucleotide && ctx->wideWorkers > 0 && stages.size() >= 2 && stages[0].kind == 0 && stages[1].kind == 0 &&
                        stages[1].cap > stages[0].cap && n > ctx->smCount;
     int wideGrid = 0;
     bool takeMain = false;
@@ -437,8 +426,7 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
             ++s;   // stage 1 ran alongside
             continue;
         }
-        if (st.kind == 3) TWL_CUDA(ctx, twl::launchTalcoWarp(matClass, a, st.grid, ctx->stream));
-        else if (st.kind == 0) TWL_CUDA(ctx, twl::launchTalcoWavefront(st.threads, st.slots, matClass, a, st.grid, ctx->stream));
+        if (st.kind == 0) TWL_CUDA(ctx, twl::launchTalcoWavefront(st.threads, st.slots, matClass, a, st.grid, ctx->stream));
         else TWL_CUDA(ctx, twl::launchTalcoGeneric(ctx->P, st.kind == 2, a, st.grid, st.kind == 1 ? twl::genericStateWords(st.cap) * sizeof(float) : 0, ctx->stream));
         ctx->lastLaunches += 1;
         if (ctx->dpTrace) {   // diagnosis only: serialises the chain and prints each stage's time and work count
@@ -517,16 +505,11 @@ int twl_align_profiles(twl_ctx *ctx, const twl_profile_pair *pairs, int n_pairs,
 int twl_set_option(twl_ctx *ctx, const char *name, int value) {
     if (!ctx || !name) return TWL_E_ARG;
     if (std::strcmp(name, "force_generic") == 0) { ctx->forceGeneric = value != 0; return TWL_OK; }
-    if (std::strcmp(name, "first_threads") == 0) { if (value != 96 && value != 128) return TWL_E_ARG; ctx->firstThreads = value; return TWL_OK; }
-    if (std::strcmp(name, "wide_threads") == 0) { if (value != 256 && value != 512) return TWL_E_ARG; ctx->wideThreads = value; return TWL_OK; }
     if (std::strcmp(name, "wide_workers") == 0) { ctx->wideWorkers = std::max(0, value); return TWL_OK; }
     if (std::strcmp(name, "dp_trace") == 0) { ctx->dpTrace = value; return TWL_OK; }
     if (std::strcmp(name, "max_ctas_per_sm") == 0) { ctx->maxCtasPerSm = std::max(0, value); return TWL_OK; }   // occupancy experiments (0 = what fits)
-    if (std::strcmp(name, "latency_shape") == 0) { ctx->latencyShape = value; return TWL_OK; }   // 0: 256x2, 1: 512x1
+    if (std::strcmp(name, "latency_shape") == 0) { if (value != 2 && value != 3) return TWL_E_ARG; ctx->latencyShape = value; return TWL_OK; }   // 2: 512x2, 3: 512x1 then 512x2
     if (std::strcmp(name, "latency_mode") == 0) { ctx->latencyMode = value; return TWL_OK; }     // -1 auto, 0 off, 1 always
-    if (std::strcmp(name, "dp_kernel") == 0) { ctx->dpKernel = value; return TWL_OK; }             // 0 auto, 1 CTA per pair, 2 warp per pair
-    if (std::strcmp(name, "warp_ctas_per_sm") == 0) { ctx->warpCtasPerSm = std::max(1, value); return TWL_OK; }
-    if (std::strcmp(name, "warp_min_pairs") == 0) { ctx->warpMinPairs = std::max(1, value); return TWL_OK; }
     return fail(ctx, TWL_E_ARG, std::string("twl_set_option: unknown option ") + name);
 }
 

@@ -78,8 +78,7 @@ struct twl_ctx {
     DevBuf<uint8_t> dTb;
     DevBuf<float> dState;
 
-    int dpKernel = 1;            // nucleotide first stage: 0 auto, 1 CTA per pair (talco_wavefront.cu), 2 warp per pair (talco_warp.cu)
-    int latencyMode = -1;        // 256x2 low-latency wavefront variant for levels with <= smCount pairs: -1 auto, 0 off, 1 always
+    int latencyMode = -1;        // low-latency wavefront shape (one CTA per SM) for levels with <= smCount pairs: -1 auto, 0 off, 1 always
     int dpTrace = 0;
     int maxCtasPerSm = 0;        // cap on resident CTAs per SM of the wavefront stages (0 = as many as fit); occupancy experiments
     int wideWorkers = 8;         // CTAs of the wide wavefront kernel that run next to the narrow one (0 = run the wide stage afterwards)
@@ -88,11 +87,7 @@ struct twl_ctx {
                                  // the rest of the context's life instead of paying the watchdog at every level
     cudaStream_t stream2 = nullptr;
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
-    int wideThreads = 512;       // second wavefront stage (1024-row window): 512 threads x 2 rows, or 256 x 4
-    int latencyShape = 2;
-    int firstThreads = 128;      // CTA size of the first wavefront stage: 128 (window 512 rows) or 96 (window 384 rows)
-    int warpCtasPerSm = 8;
-    int warpMinPairs = 2048;
+    int latencyShape = 2;        // 2: 512 threads x 2 rows; 3: 512 x 1 first, 512 x 2 for pairs whose band outgrows 512 rows
     bool forceGeneric = false;   // route nucleotide batches through the generic kernel (A/B parity + benchmarking)
     float lastMs = -1.0f;
     int lastLaunches = 0;
