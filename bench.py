@@ -266,7 +266,12 @@ def run_cli_config(name, argv, rows_expected, golden_md5, cpu_argv=None, cpu_not
             if res.returncode != 0:
                 return {"unavailable": f"CLI failed: {res.stderr[-300:]}"}
             st = parse_stats(res.stderr) or {}
-            md5 = hashlib.md5(open(out, "rb").read()).hexdigest()
+            h = hashlib.md5()
+            with open(out, "rb") as fh:
+                for blk in iter(lambda: fh.read(1 << 24), b""):
+                    h.update(blk)
+            md5 = h.hexdigest()
+            os.remove(out)
             if best is None or wall < best["wall_s"]:
                 best = {"wall_s": wall, "stats": st, "md5": md5}
         cpu = None
@@ -276,7 +281,7 @@ def run_cli_config(name, argv, rows_expected, golden_md5, cpu_argv=None, cpu_not
             res = subprocess.run([REF_CLI] + cpu_argv + ["-o", os.path.join(tmp, "cpu.aln"), "-d", os.path.join(tmp, "cputmp"), "-C", str(threads)],
                                  cwd=tmp, capture_output=True, text=True)
             cpu_wall = time.perf_counter() - t0
-            n_cpu = open(os.path.join(tmp, "cpu.aln"), "rb").read().count(b">") if res.returncode == 0 else 0
+            n_cpu = sum(blk.count(b">") for blk in iter(lambda f=open(os.path.join(tmp, "cpu.aln"), "rb"): f.read(1 << 24), b"")) if res.returncode == 0 else 0
             cpu = {"value": n_cpu / cpu_wall, "unit": "sequences/s", "cores": threads, "kind": "reference", "wall_s": cpu_wall,
                    "sample": cpu_note or "the same input through oracle/_ref/twilight_ref (unmodified reference CLI, CPU path)"}
     st = best["stats"]
@@ -314,6 +319,14 @@ def run_named_configs(flush):
             cpu_note="the 10^3-leaf rung of the same generator (rna_1k) through oracle/_ref/twilight_ref: the 10^4-leaf run takes the CPU "
                      f"{gold_syn['rna_10k_default']['ref_seconds_8_threads']} s on 8 threads (tests/golden/cli_synth_md5.json)", repeats=1)
         out["C3_rna_10k_cli"]["workload"] = "synthetic RNA, 10^4 leaves x 1.5 kb, random tree (C3 ladder rung), default mode through the drop-in CLI"
+        if "rna_100k_default" in gold_syn:    # the 10^5 rung: ~20 minutes on the CPU reference (golden md5 recorded once), seconds here
+            huge = synth.make_dataset("rna_100k", tmp)
+            out["C3_rna_100k_cli"] = run_cli_config("rna_100k", ["-t", huge + ".nwk", "-i", huge + ".fa"], 100000, gold_syn["rna_100k_default"]["md5"], repeats=1)
+            out["C3_rna_100k_cli"]["workload"] = "synthetic RNA, 10^5 leaves x 1.5 kb, random tree (C3 ladder rung), default mode through the drop-in CLI"
+            out["C3_rna_100k_cli"]["cpu_baseline"] = {
+                "value": 100000 / gold_syn["rna_100k_default"]["ref_seconds_8_threads"], "unit": "sequences/s", "cores": 8, "kind": "reference",
+                "sample": "NOT timed in this run: oracle/_ref/twilight_ref on the same input, 8 threads of the build container "
+                          f"({gold_syn['rna_100k_default']['ref_seconds_8_threads']} s, tests/golden/cli_synth_md5.json)"}
     out["C4_level_30kb"] = run_level_config(
         "C4", "dna", 592, 29700, 3, 2, flush, 16, dict(divergence=0.004, indel_rate=0.002, members=(1, 2, 4)),
         "one guide-tree level of 592 node pairs (4 per SM) of SARS-CoV-2-length genomes (~29.7 kb, 1-4 members per node, tip identity ~99.6 %): "

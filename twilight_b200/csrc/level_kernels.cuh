@@ -12,7 +12,7 @@
 namespace twl {
 
 constexpr int kLvlThreads = 256;
-constexpr int kPathChunk = 1024;
+constexpr int kPathChunk = 2048;   // path ops per block of rowUpdateKernel (8 per thread): most pairs of a ~1.5 kb level are one block
 
 // One side (node) of a pair as the level kernels see it.
 struct DevSide {
@@ -779,33 +779,43 @@ __global__ void __launch_bounds__(kLvlThreads) rowUpdateKernel(const DevUpdate *
     // index), so per row it reads the two aligned words that hold them (rows are 16-byte aligned and over-allocated), picks the
     // bytes with one byte permutation whose selector depends on the ops only, and writes one aligned 32-bit word.
     {
+        constexpr int WORDS = PER / 4;
         const int e0 = threadIdx.x * PER;
-        unsigned selR = 0, selQ = 0;          // per output byte: index 0..3 into the source window, or 4 = '-'
-        int pr = 0, pq = 0;
+        unsigned selR[WORDS], selQ[WORDS];     // per output byte: index 0..3 into the word's source window, or 4 = '-'
+        int firstR[WORDS], firstQ[WORDS];
 #pragma unroll
-        for (int e = 0; e < PER; ++e) {
-            const int op = ops[e0 + e];
-            const bool takeR = (op == 0 || op == 2), takeQ = (op == 0 || op == 1);
-            selR |= static_cast<unsigned>(takeR ? pr : 4) << (4 * e);
-            selQ |= static_cast<unsigned>(takeQ ? pq : 4) << (4 * e);
-            pr += takeR; pq += takeQ;
+        for (int w = 0; w < WORDS; ++w) {
+            unsigned sr = 0, sq = 0;
+            int pr = 0, pq = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int op = ops[e0 + 4 * w + e];
+                const bool takeR = (op == 0 || op == 2), takeQ = (op == 0 || op == 1);
+                sr |= static_cast<unsigned>(takeR ? pr : 4) << (4 * e);
+                sq |= static_cast<unsigned>(takeQ ? pq : 4) << (4 * e);
+                pr += takeR; pq += takeQ;
+            }
+            selR[w] = sr; selQ[w] = sq;
+            firstR[w] = srcR[e0 + 4 * w]; firstQ[w] = srcQ[e0 + 4 * w];
         }
-        const int firstR = srcR[e0], firstQ = srcQ[e0];
-        const bool whole = e0 + PER <= nHere;
         for (int m = blockIdx.z; m < u.nRef + u.nQry; m += gridDim.z) {
             const bool isRef = m < u.nRef;
             const char *in = rowIn[u.memberOff + m];
             char *out = rowOut[u.memberOff + m] + k0;
-            const int first = isRef ? firstR : firstQ;
-            if (whole) {
-                const unsigned *w = reinterpret_cast<const unsigned *>(in) + (first >> 2);
-                const unsigned window = __funnelshift_r(w[0], w[1], 8 * (first & 3));
-                *reinterpret_cast<unsigned *>(out + e0) = __byte_perm(window, 0x2D2D2D2Du, isRef ? selR : selQ);
-            } else {
-                for (int e = e0; e < nHere; ++e) {
-                    const int op = ops[e];
-                    const bool take = (op == 0) || (op == (isRef ? 2 : 1));
-                    out[e] = take ? in[isRef ? srcR[e] : srcQ[e]] : '-';
+#pragma unroll
+            for (int w = 0; w < WORDS; ++w) {
+                const int eW = e0 + 4 * w;
+                if (eW + 4 <= nHere) {
+                    const int first = isRef ? firstR[w] : firstQ[w];
+                    const unsigned *src = reinterpret_cast<const unsigned *>(in) + (first >> 2);
+                    const unsigned window = __funnelshift_r(src[0], src[1], 8 * (first & 3));
+                    *reinterpret_cast<unsigned *>(out + eW) = __byte_perm(window, 0x2D2D2D2Du, isRef ? selR[w] : selQ[w]);
+                } else {
+                    for (int e = eW; e < min(eW + 4, nHere); ++e) {
+                        const int op = ops[e];
+                        const bool take = (op == 0) || (op == (isRef ? 2 : 1));
+                        out[e] = take ? in[isRef ? srcR[e] : srcQ[e]] : '-';
+                    }
                 }
             }
         }
