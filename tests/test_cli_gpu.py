@@ -24,3 +24,21 @@ def test_fasta_byte_identical(name, tmp_path):
     assert len(data) == GOLD[name]["bytes"], log[-1500:]
     assert hashlib.md5(data).hexdigest() == GOLD[name]["md5"], log[-1500:]
     assert "did not match" not in log
+
+
+def test_out_of_memory_spills_and_retries(tmp_path):
+    """A level that fails with TWL_E_NOMEM (injected at the 3rd and the 9th level call) makes the adapter send every dirty row
+    back to the host, empty the device row store and retry the level with its rows re-sent: same bytes as an undisturbed run."""
+    import subprocess
+    if not os.path.exists(CLI) or not os.path.isdir(DATA):
+        pytest.skip("build/twilight_b200 or oracle/_ref/dataset missing")
+    from tests.cli_scenarios import SCENARIOS
+    name = "rnasim_default"
+    args = [a.replace("{D}", DATA) for a in SCENARIOS[name]]
+    for inject in ("3", "9"):
+        out = str(tmp_path / f"o{inject}.aln")
+        env = dict(os.environ, TWL_OPTIONS=f"inject_nomem={inject}")
+        res = subprocess.run([CLI] + args + ["-o", out, "-d", str(tmp_path / f"tmp{inject}")], cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=900)
+        assert res.returncode == 0, res.stderr[-1500:]
+        assert "spilling the row store" in res.stderr
+        assert hashlib.md5(open(out, "rb").read()).hexdigest() == GOLD[name]["md5"]

@@ -181,3 +181,38 @@ def test_empty_node(empty_side):
     assert set(out.path.tolist()) == ({1} if empty_side == 0 else {2})
     assert ctx.rows_download(list(range(4))) == rec.merged.rows
     ctx.close()
+
+
+def test_failed_level_leaves_the_row_store_untouched():
+    """twl_align_level is all or nothing: a call that fails after its kernels ran (fault injection: twl_set_option
+    inject_nomem) reports TWL_E_NOMEM, every row still reads as before, and the same level then aligns to the oracle's result."""
+    import twilight_b200
+    rng = np.random.default_rng(12)
+    cfg = ol.TalcoCfg()
+    ctx = twilight_b200.Context()
+    fams = []
+    ids, rows, pairs, states = [], [], [], []
+    for k in range(6):
+        anc = rng.choice(LETTERS, 500 + 40 * k)
+        fa, fb = _family(anc, 3, rng), _family(synth._mutate(anc, 0.08, rng, LETTERS, 0.05), 2, rng)
+        sides = []
+        for fr in (fa, fb):
+            mine = list(range(len(ids), len(ids) + len(fr)))
+            ids += mine
+            rows += fr
+            sides.append(twilight_b200.NodeSideIn(mine, len(fr[0]), len(fr), float(len(fr))))
+            states.append(ref_msa.NodeState(fr, np.ones(len(fr), np.float32), len(fr[0]), len(fr), float(len(fr))))
+        pairs.append(twilight_b200.LevelPairIn(sides[0], sides[1]))
+    ctx.rows_upload(ids, rows, np.ones(len(ids), np.float32))
+    ctx.set_option("inject_nomem", 1)
+    with pytest.raises(twilight_b200.TwilightError, match="NOMEM|out-of-memory"):
+        ctx.align_level(pairs)
+    assert ctx.rows_download(ids) == rows
+    outs = ctx.align_level(pairs)
+    want_rows = []
+    for k, o in enumerate(outs):
+        rec = ref_msa.align_pair("n", cfg, states[2 * k], states[2 * k + 1])
+        assert o.status == rec.error == 0 and np.array_equal(o.path, rec.aln_w)
+        want_rows += rec.merged.rows
+    assert ctx.rows_download(ids) == want_rows
+    ctx.close()

@@ -507,6 +507,7 @@ int twl_set_option(twl_ctx *ctx, const char *name, int value) {
     if (std::strcmp(name, "force_generic") == 0) { ctx->forceGeneric = value != 0; return TWL_OK; }
     if (std::strcmp(name, "wide_workers") == 0) { ctx->wideWorkers = std::max(0, value); return TWL_OK; }
     if (std::strcmp(name, "dp_trace") == 0) { ctx->dpTrace = value; return TWL_OK; }
+    if (std::strcmp(name, "inject_nomem") == 0) { ctx->injectNomem = std::max(0, value); return TWL_OK; }
     if (std::strcmp(name, "max_ctas_per_sm") == 0) { ctx->maxCtasPerSm = std::max(0, value); return TWL_OK; }   // occupancy experiments (0 = what fits)
     if (std::strcmp(name, "latency_shape") == 0) { if (value != 2 && value != 3) return TWL_E_ARG; ctx->latencyShape = value; return TWL_OK; }   // 2: 512x2, 3: 512x1 then 512x2
     if (std::strcmp(name, "latency_mode") == 0) { ctx->latencyMode = value; return TWL_OK; }     // -1 auto, 0 off, 1 always

@@ -80,6 +80,8 @@ struct twl_ctx {
 
     int latencyMode = -1;        // low-latency wavefront shape (one CTA per SM) for levels with <= smCount pairs: -1 auto, 0 off, 1 always
     int dpTrace = 0;
+    int injectNomem = 0;         // fault injection for tests: the n-th twl_align_level call from now fails with TWL_E_NOMEM after its last
+                                 // chunk has already flipped row buffers (exercises the rollback and the caller's spill-and-retry path)
     int maxCtasPerSm = 0;        // cap on resident CTAs per SM of the wavefront stages (0 = as many as fit); occupancy experiments
     int wideWorkers = 8;         // CTAs of the wide wavefront kernel that run next to the narrow one (0 = run the wide stage afterwards)
     PinBuf<int> hWatchdog;       // copy of the device flag a wide worker sets when its 20 ms watchdog fires: the two kernels were not

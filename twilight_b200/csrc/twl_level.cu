@@ -957,7 +957,11 @@ int twl_align_level(twl_ctx *ctx, const twl_level_pair *pairs, int n_pairs, int 
         }
         const int rc = (ctx->P == 6) ? runLevelChunk<6>(ctx, L, pairs, begin, end, current_task, gappy_threshold, cache_threshold, paths, results, chunkNo, journal)
                                      : runLevelChunk<22>(ctx, L, pairs, begin, end, current_task, gappy_threshold, cache_threshold, paths, results, chunkNo, journal);
-        if (rc != TWL_OK) {
+        int rcEff = rc;
+        if (rc == TWL_OK && end >= n_pairs && ctx->injectNomem > 0 && --ctx->injectNomem == 0)
+            rcEff = twlFail(ctx, TWL_E_NOMEM, "twl_align_level: injected out-of-memory failure (twl_set_option inject_nomem)");
+        if (rcEff != TWL_OK) {
+            const int rc = rcEff;
             const std::string why = ctx->error;
             cudaStreamSynchronize(ctx->stream);
             for (auto it = journal.rbegin(); it != journal.rend(); ++it) {
