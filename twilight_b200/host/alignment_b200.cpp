@@ -7,8 +7,9 @@
 // getConsensus, removeGappyColumns, calculatePSGP, Talco_xdrop::Align_freq, addGappyColumnsBack, updateFrequency and the
 // row rewrite of updateAlignment) runs on the B200 in ONE call per level, twl_align_level. The member rows live in HBM
 // for the whole progressive alignment of a subtree: a row is uploaded once, when its leaf is first aligned, rewritten
-// on the device at every level, and copied back to SequenceInfo::alnStorage once — when its node is parked behind a
-// group id (helper.cpp:479-500; from then on only its path is composed) or when msaOnSubtree ends. Per level the host
+// on the device at every level — including the rows of nodes the reference would "park" behind a group id
+// (helper.cpp:479-500), so the final MSA is materialised in HBM — and copied back to SequenceInfo::alnStorage once, when
+// msaOnSubtree ends (with TWL_PARK=1: when its node is parked). Per level the host
 // does O(pairs + member ids) bookkeeping: node fields, deferral (fallback2cpu), parking, path composition for
 // negative ids. No alignment arithmetic runs on the host, and there is no CPU fallback: if the CUDA library cannot
 // initialise, the process aborts with a message.
@@ -172,6 +173,14 @@ void downloadRows(SequenceDB *database, const std::vector<int32_t> &ids) {
     RowState &rs = rowState();
     Devices &D = devices();
     constexpr size_t kSliceBytes = static_cast<size_t>(512) << 20;
+    // SequenceInfo::memCheck (sequencedb.cpp:57-76) reallocates and zero-fills both buffers of a row that outgrew them: for a
+    // final MSA that is several GB of host writes, so it runs on all host threads like the reference's own update loops
+    tbb::parallel_for(tbb::blocked_range<size_t>(0, ids.size()), [&](tbb::blocked_range<size_t> range) {
+        for (size_t i = range.begin(); i < range.end(); ++i) {
+            auto *seq = database->sequences[ids[i]];
+            seq->memCheck(seq->len);
+        }
+    });
     for (size_t d = 0; d < D.dev.size(); ++d) {
         std::vector<int32_t> mine;
         for (int32_t id : ids) if (rs.rows[id].dev == static_cast<int8_t>(d)) mine.push_back(id);
@@ -181,7 +190,6 @@ void downloadRows(SequenceDB *database, const std::vector<int32_t> &ids) {
             std::vector<char *> dst;
             while (end < mine.size() && (end == at || bytes < kSliceBytes)) {
                 auto *seq = database->sequences[mine[end]];
-                seq->memCheck(seq->len);                                   // sequencedb.cpp:57-76 (host len already tracks the device)
                 dst.push_back(seq->alnStorage[seq->storage]);
                 bytes += static_cast<size_t>(seq->len);
                 ++end;
@@ -489,9 +497,16 @@ void alignmentKernel_B200_level(Tree *tree, NodePairVec &nodes, SequenceDB *data
         first->alnWeight += second->alnWeight;
         for (auto idx : second->seqsIncluded) first->seqsIncluded.push_back(idx);
         second->seqsIncluded.clear();
-        // parking of >1000 sequences behind one group id, helper.cpp:479-500: from now on only the group's path is composed,
-        // the rows themselves are final until progressive::updateAlignment expands them -> they go back to the host now
-        if (first->seqsIncluded.size() > alignment_helper::_UPDATE_SEQ_TH && !first->msaFreq.empty() && task != 2) {
+        // Parking of >1000 sequences behind one group id (helper.cpp:479-500) is a host-memory-bandwidth optimisation of the
+        // reference: the rows of a big node stop being rewritten, only one path per group is composed, and
+        // progressive::updateAlignment (progressive.cpp:194-230) expands the rows through the composed path at the end. On the
+        // device rewriting rows is an HBM-speed kernel, so by default nothing is parked: every member row is rewritten at every
+        // level and the final MSA is materialised in HBM when the last level returns (the host's expansion loop finds nothing
+        // to do, no path ever crosses PCIe for it). The final bytes are the same — composing paths and applying them one after
+        // the other are the same function. TWL_PARK=1 restores the reference's parking (rows of a parked node go back to the
+        // host at that moment), which keeps device memory at ~4x the *current* row lengths instead of the final ones.
+        static const bool park = [] { const char *e = std::getenv("TWL_PARK"); return e && std::atoi(e) != 0; }();
+        if (park && first->seqsIncluded.size() > alignment_helper::_UPDATE_SEQ_TH && !first->msaFreq.empty() && task != 2) {
             int seqCount = 0, firstSeqID = 0;
             for (auto idx : first->seqsIncluded)
                 if (idx > 1) { if (firstSeqID == 0) firstSeqID = -idx; seqCount++; }
