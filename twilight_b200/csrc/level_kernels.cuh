@@ -122,11 +122,15 @@ __global__ void __launch_bounds__(kProfThreads) profileBuildNtKernel(const DevSi
     __shared__ float acc[P][kProfCols][kProfThreads];
     __shared__ unsigned char lut[256];
     const DevSide sd = sides[blockIdx.x];
-    const int t0 = (blockIdx.y * kProfThreads + threadIdx.x) * kProfCols;     // first of this thread's columns
     if (blockIdx.y * kProfThreads * kProfCols >= sd.alnLen) return;
     for (int c = threadIdx.x; c < 256; c += kProfThreads) lut[c] = static_cast<unsigned char>(letterIndexNt(static_cast<unsigned char>(c)));
+    // grid.y column tiles of 512 columns; with many sides the host launches grid.y = 1 and the block walks the tiles of its side
+    // (the side descriptor and the member pointers are fetched once, fewer and fatter blocks)
+    for (int tile = blockIdx.y; tile * kProfThreads * kProfCols < sd.alnLen; tile += gridDim.y) {
+    const int t0 = (tile * kProfThreads + threadIdx.x) * kProfCols;           // first of this thread's columns
     const int nHere = min(kProfCols, sd.alnLen - t0);                          // <= 0: nothing to do for this thread
     float col[kProfCols][P];
+    __syncthreads();                                                       // the previous tile's accumulators have been read
     if (sd.freqInOff >= 0) {                                               // helper.cpp:16-21
 #pragma unroll
         for (int c = 0; c < kProfCols; ++c)
@@ -176,7 +180,7 @@ __global__ void __launch_bounds__(kProfThreads) profileBuildNtKernel(const DevSi
 #pragma unroll
             for (int v = 0; v < P; ++v) col[c][v] = acc[v][c][threadIdx.x];
     }
-    if (nHere <= 0) return;
+    if (nHere <= 0) continue;
     float *dst = raw + sd.rawOff + static_cast<long long>(t0) * P;
     float *fdst = (sd.freqOutOff >= 0) ? freqOut + sd.freqOutOff + static_cast<long long>(t0) * P : nullptr;
     const char *letters = "ACGTN";
@@ -219,6 +223,7 @@ __global__ void __launch_bounds__(kProfThreads) profileBuildNtKernel(const DevSi
 #pragma unroll
         for (int c = 0; c < kProfCols; ++c)
             if (c < nHere) { cons[sd.consOff + t0 + c] = static_cast<char>((packed >> (8 * c)) & 0xFFu); gapCount[sd.consOff + t0 + c] = g4[c]; }
+    }
     }
 }
 

@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 640 / NT : 1)) talcoWavefront
     const int marker = a.marker;
     const int rho0 = tid * kSlots;
     if (a.coMode == 1 && tid == 0) atomicAdd(a.heartbeat, 1);
+    if (a.coMode == 2 && tid == 0 && a.arrived) atomicAdd(a.arrived, 1);
 
     for (;;) {
         __syncthreads();
@@ -662,6 +663,20 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 640 / NT : 1)) talcoWavefront
         }
     }
     if (a.coTrace && tid == 0 && blockIdx.x == 0) a.coTrace[4 * (*a.nWorkPtr) + (a.coMode == 2 ? 1 : 0)] = globalTimerNs();
+}
+
+// Co-run gate: one thread, launched on the narrow kernel's stream right before it. The narrow grid is sized to leave `want` SMs to
+// the wide workers, but the block scheduler spreads its CTAs over every SM unless those SMs are already taken: without the gate
+// the two launches race, and when the narrow kernel wins no wide CTA (512 threads, a whole SM) fits until the narrow kernel
+// ends — every hand-over then waits for the end of the stage (measured: +6 ms on a 62 ms level). The gate returns as soon as
+// the wide CTAs have counted themselves in, or after 300 us (kernels serialised by a profiler: nothing will arrive).
+__global__ void coRunGateKernel(const int *arrived, int want) {
+    const unsigned long long t0 = globalTimerNs();
+    while (*reinterpret_cast<volatile const int *>(arrived) < want && globalTimerNs() - t0 < 300000ull) __nanosleep(200);
+}
+cudaError_t launchCoRunGate(const int *arrived, int want, cudaStream_t stream) {
+    coRunGateKernel<<<1, 1, 0, stream>>>(arrived, want);
+    return cudaGetLastError();
 }
 
 // The wavefront kernels hold bands of up to W-(KS-1) cells (the window base is rounded down to a multiple of KS).

@@ -20,6 +20,7 @@ int wavefrontBandCapacity(int threads, int slots);
 int wavefrontWindow(int threads, int slots);
 int nucleotideMatrixClass(const float *score5x5);
 cudaError_t launchTalcoWavefront(int threads, int slots, int matClass, const TalcoArgs &args, int grid, cudaStream_t stream);
+cudaError_t launchCoRunGate(const int *arrived, int want, cudaStream_t stream);
 int wavefrontMaxCtasPerSm(int threads, int slots, int matClass);
 cudaError_t launchDivSelfTest(const float *num, const float *den, int n, int *mismatches, cudaStream_t stream);
 } // namespace twl
@@ -306,7 +307,9 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
         stages[1].grid = wideGrid;
         stages[0].grid = std::min(n, (ctx->smCount - wideGrid) * perSm);
         if (!ctx->stream2) {
-            TWL_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+            int least = 0, greatest = 0;   // the wide workers' stream gets the highest priority: their CTAs are placed first when both kernels are pending
+            TWL_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&least, &greatest));
+            TWL_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, greatest));
             TWL_CUDA(ctx, cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming));
             TWL_CUDA(ctx, cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming));
         }
@@ -368,6 +371,7 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
             w.mainDone = ctx->dCounters.ptr + 14;
             w.heartbeat = ctx->dCounters.ptr + 15;
             w.watchdog = ctx->dCounters.ptr + 13;
+            w.arrived = ctx->dCounters.ptr + 12;
             w.feedList = ctx->dOverflow.ptr;
             w.feedCount = ctx->dCounters.ptr + 3;
             w.feedCursor = ctx->dCounters.ptr + 2;
@@ -386,12 +390,13 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
             TWL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->evFork, 0));
             TWL_CUDA(ctx, twl::launchTalcoWavefront(sw.threads, sw.slots, matClass, w, sw.grid, ctx->stream2));
             TWL_CUDA(ctx, cudaEventRecord(ctx->evJoin, ctx->stream2));
+            TWL_CUDA(ctx, twl::launchCoRunGate(ctx->dCounters.ptr + 12, sw.grid, ctx->stream));   // the narrow kernel starts once the wide workers are resident
             a.coMode = 1;
             a.mainDone = w.mainDone; a.heartbeat = w.heartbeat; a.feedList = w.feedList; a.feedCount = w.feedCount; a.feedCursor = w.feedCursor;
             a.overflowList = nullptr; a.overflowCount = nullptr;
             TWL_CUDA(ctx, twl::launchTalcoWavefront(st.threads, st.slots, matClass, a, st.grid, ctx->stream));
             TWL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
-            ctx->lastLaunches += 2;
+            ctx->lastLaunches += 3;   // wide workers, gate, narrow kernel
             if (dTrace) {
                 cudaStreamSynchronize(ctx->stream);
                 std::vector<unsigned long long> t(4 * (static_cast<size_t>(n) + 1));

@@ -82,6 +82,8 @@ struct TalcoArgs {
     int coTakeBelow;         // mode 2: also take main-queue entries with index below this (0 = never). Large batches only, and not
                              // the last wave, so that pairs handed over near the end find an idle wide worker
     int *mainDone;           // pairs of the main queue that are completely finished (either kernel)
+    int *arrived;            // mode 2: wide CTAs count themselves in when they start; the host launches the narrow kernel behind a gate
+                             // that waits for this count, so the wide workers hold their SMs before the narrow CTAs fill the machine
     int *watchdog;           // set by a wide worker that gave up waiting (kernels were not co-scheduled): the host then stops co-running
     int *heartbeat;          // bumped by the narrow kernel at every tile: lets a waiting wide worker tell "still running" from
                              // "not running at all" (kernels serialised by a profiler or CUDA_LAUNCH_BLOCKING)

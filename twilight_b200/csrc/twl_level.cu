@@ -712,7 +712,9 @@ int runLevelChunkImpl(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pair
     // ---- phase 1: profiles + consensus (+ msaFreq cache); phase 2: gappy-column compaction + PSGP + DP packing
     TWL_CUDA(ctx, cudaEventRecord(L->ev[0], ctx->stream));
     if (P == 6) {
-        dim3 grid(nSides, std::max(1, (maxLen + kProfThreads * kProfCols - 1) / (kProfThreads * kProfCols)));
+        // many sides: one block per side walks its column tiles; few sides: one block per tile for parallelism
+        const int tiles = std::max(1, (maxLen + kProfThreads * kProfCols - 1) / (kProfThreads * kProfCols));
+        dim3 grid(nSides, (nSides >= 8 * ctx->smCount) ? 1 : tiles);
         profileBuildNtKernel<<<grid, kProfThreads, 0, ctx->stream>>>(L->dSides.ptr, L->dRowIn.ptr, L->dRowW.ptr, L->dRaw.ptr, L->dCons.ptr,
                                                                     L->dFreq.ptr, L->dFreq.ptr, L->dGap.ptr);
         TWL_CUDA(ctx, cudaGetLastError());
