@@ -65,3 +65,22 @@ def test_synthetic_fasta_byte_identical(name, data_dir, tmp_path):
     assert rep.get("same_rows") and rep.get("same_residues"), rep
     assert 1.0 - rep["sp"] <= SP_TC_TOLERANCE and 1.0 - rep["tc"] <= SP_TC_TOLERANCE, rep
     pytest.fail(f"{name}: within the SP/TC tolerance but not byte-identical: {rep}")
+
+
+def test_reference_style_parking_is_identical_too(data_dir, tmp_path):
+    """By default the adapter parks nothing (the device keeps rewriting the rows of big nodes, the final MSA is materialised
+    in HBM). TWL_PARK=1 restores the reference's parking of > 1000 sequences behind a group id (alignment-helper.cpp:479-500):
+    rows go back to the host when their node is parked, paths are composed on the host and progressive::updateAlignment expands
+    them at the end. Both must write the reference's bytes."""
+    import subprocess
+    if not os.path.exists(CLI) or "rna_3k_default" not in GOLD:
+        pytest.skip("build/twilight_b200 or golden entry missing")
+    prefix = dataset("rna_3k", data_dir)
+    out = str(tmp_path / "parked.aln")
+    env = dict(os.environ, TWL_PARK="1", TWL_STATS="1")
+    res = subprocess.run([CLI, "-t", prefix + ".nwk", "-i", prefix + ".fa", "-o", out, "-d", str(tmp_path / "tmp")], cwd=str(tmp_path), env=env,
+                         capture_output=True, text=True, timeout=1800)
+    assert res.returncode == 0, res.stderr[-1500:]
+    assert md5_file(out) == GOLD["rna_3k_default"]["md5"]
+    stats = json.loads([l for l in res.stderr.splitlines() if l.startswith("[twl-stats]")][-1][len("[twl-stats] "):])
+    assert stats["d2h_row_bytes"] < GOLD["rna_3k_default"]["bytes"]      # parked rows went back at their parked (shorter) length
