@@ -42,8 +42,12 @@ struct WaveShared {
 
 // KS = rows per thread: 4 for throughput (W = 4*NT); 2 with NT = 256 for levels with few pairs, where a CTA runs alone on
 // its SM and the per-thread instruction stream, not the issue rate, sets the time of a diagonal.
-template <int NT, int MC, int KS>
-__global__ void __launch_bounds__(NT, (NT <= 128 ? 640 / NT : 1)) talcoWavefrontKernel(const TalcoArgs a) {
+// SC = score source: 0 = nucleotide profiles, similarity computed on the fly (scoreDiagonal); 1 = any alphabet, similarity read from the
+// pair's anti-diagonal-major matrix written by simMatrixKernel (talco_sim.cu) and gap penalties from its compact array — the
+// protein path: the 21 x 21 contraction is done once per cell by a dependency-free kernel at full occupancy, and the recurrence
+// runs register-resident here instead of in the shared-memory generic kernel.
+template <int NT, int MC, int KS, int SC>
+__global__ void __launch_bounds__(NT, (NT <= 128 ? (SC ? 1024 : 640) / NT : 1)) talcoWavefrontKernel(const TalcoArgs a) {
     constexpr int kSlots = KS;
     constexpr int W = NT * kSlots;
     constexpr int NW = NT / 32;
@@ -130,6 +134,13 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 640 / NT : 1)) talcoWavefront
         const int divMode = (denom == 1.0f) ? 0 : (((__float_as_int(denom) & 0x7fffff) == 0x7fffff) ? 2 : 1);
         const float gapChar = pr.gapChar;
         const int kind = pr.pad;   // kRefOneHot | kQryOneHot
+        const float *simBase = nullptr;
+        const float2 *gapRef = nullptr;
+        int simStride = 0;
+        if (SC == 1) {
+            const DevSim si = a.simInfo[pairIdx];
+            simBase = a.sim + si.simOff; gapRef = reinterpret_cast<const float2 *>(a.sim + si.gapOff); simStride = si.stride;
+        }
         int refOff = 0, qryOff = 0, tile = 0, outPos = 0, status = 0;
         unsigned long long cells = 0, diagonals = 0;
         bool lastTile = false;
@@ -179,7 +190,7 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 640 / NT : 1)) talcoWavefront
             int convValue = 0, prevConvS = -1, lastK = 0, error = 0;
             unsigned tileCells = 0;
             const int nDiag = refLen + qryLen - 1;
-            const float4 *refX = reinterpret_cast<const float4 *>(refCols), *refY = refX + 4 * static_cast<long long>(pr.refN4);
+            const float4 *refX = reinterpret_cast<const float4 *>(refCols);
             const float4 *qryX = reinterpret_cast<const float4 *>(qryCols), *qryY = qryX + 4 * static_cast<long long>(pr.qryN4);
             const int prevWarp = (warp + NW - 1) % NW;
             int g0 = 1;
@@ -199,7 +210,7 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 640 / NT : 1)) talcoWavefront
                 tileCells += static_cast<unsigned>(width);
                 const float pruneBelow = __fsub_rn(maxScore, xdropF);
 
-                if ((k & 3) == 0 && warp == 0) {
+                if (SC == 0 && (k & 3) == 0 && warp == 0) {
                     // Warm L1 for the lines the band edges will touch a few diagonals from now: one 128 B line holds 8 consecutive
                     // float4 of one stream = a span of 32 columns, and the leading edge moves one column per diagonal, so every
                     // fourth diagonal the 8 streams of each side are touched once (lanes 0-7 reference columns, 8-15 query rows).
@@ -225,6 +236,11 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 640 / NT : 1)) talcoWavefront
                     rowBase = iBase;
 #pragma unroll
                     for (int c = 0; c < kSlots; ++c) {
+                        if (SC == 1) {   // only the row's gap penalties: columns are P + 2 = 24 floats, penalties last
+                            const float2 g = __ldg(reinterpret_cast<const float2 *>(qryCols + static_cast<size_t>(qryOff + min(iBase + c, qryLen - 1)) * 24 + 22));
+                            gOpQ[c] = g.x; gExQ[c] = g.y;
+                            continue;
+                        }
                         const long long at = ntColIndex(qryOff + min(iBase + c, qryLen - 1), pr.qryN4);
                         const float4 x = __ldg(qryX + at);
                         const float4 y = __ldg(qryY + at);
@@ -261,7 +277,20 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? 640 / NT : 1)) talcoWavefront
 
                 if (__any_sync(0xffffffffu, anyAct)) {
                     float num[kSlots], gOpR[kSlots], gExR[kSlots];
-                    scoreDiagonal<MC, KS>(a, refX, pr.refN4, refOff + k, iBase, q, gapChar, kind, divMode, denom, rcp, num, gOpR, gExR);
+                    if (SC == 1) {
+                        // cell (row i, column j) of the pair lives at [i + j][i]: the rows of a thread are adjacent words, the rows of a
+                        // warp one contiguous run. Slots that are not live may read beyond the matrix (padded, values discarded).
+                        const float *src = simBase + static_cast<long long>(refOff + qryOff + k) * simStride + (qryOff + iBase);
+                        const float2 *gsrc = gapRef + (refOff + k - iBase);
+#pragma unroll
+                        for (int c = 0; c < kSlots; ++c) {
+                            num[c] = __ldg(src + c);
+                            const float2 g = __ldg(gsrc - c);
+                            gOpR[c] = g.x; gExR[c] = g.y;
+                        }
+                    } else {
+                        scoreDiagonal<MC, KS>(a, refX, pr.refN4, refOff + k, iBase, q, gapChar, kind, divMode, denom, rcp, num, gOpR, gExR);
+                    }
 
                     // match candidates: H[k-2][i-1] + sim when the diagonal neighbour is inside its band ...
                     float match[kSlots];
@@ -580,24 +609,33 @@ cudaError_t launchDivSelfTest(const float *num, const float *den, int n, int *mi
 // supported instantiations: (threads, slots) = (128,4) throughput, (512,2) wide band / low latency, (512,1) narrow-band low latency
 template <int MC>
 static cudaError_t launchMc(int threads, int slots, const TalcoArgs &args, int grid, cudaStream_t stream) {
-    if (threads == 128 && slots == 4) talcoWavefrontKernel<128, MC, 4><<<grid, 128, 0, stream>>>(args);
-    else if (threads == 512 && slots == 1) talcoWavefrontKernel<512, MC, 1><<<grid, 512, 0, stream>>>(args);
-    else if (threads == 512 && slots == 2) talcoWavefrontKernel<512, MC, 2><<<grid, 512, 0, stream>>>(args);
+    if (threads == 128 && slots == 4) talcoWavefrontKernel<128, MC, 4, 0><<<grid, 128, 0, stream>>>(args);
+    else if (threads == 512 && slots == 1) talcoWavefrontKernel<512, MC, 1, 0><<<grid, 512, 0, stream>>>(args);
+    else if (threads == 512 && slots == 2) talcoWavefrontKernel<512, MC, 2, 0><<<grid, 512, 0, stream>>>(args);
     else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
 
+// matClass: 0 / 1 nucleotide (see nucleotideMatrixClass); -1: scores come from the similarity matrix (protein path, SC = 1)
 cudaError_t launchTalcoWavefront(int threads, int slots, int matClass, const TalcoArgs &args, int grid, cudaStream_t stream) {
+    if (matClass < 0) {
+        if (threads == 128 && slots == 4) talcoWavefrontKernel<128, 0, 4, 1><<<grid, 128, 0, stream>>>(args);
+        else if (threads == 512 && slots == 2) talcoWavefrontKernel<512, 0, 2, 1><<<grid, 512, 0, stream>>>(args);
+        else return cudaErrorInvalidValue;
+        return cudaGetLastError();
+    }
     return matClass == 1 ? launchMc<1>(threads, slots, args, grid, stream) : launchMc<0>(threads, slots, args, grid, stream);
 }
 
 int wavefrontMaxCtasPerSm(int threads, int slots, int matClass) {
     int n = 0;
-#define TWL_OCC(NT_, MC_, KS_) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, talcoWavefrontKernel<NT_, MC_, KS_>, NT_, 0)
-    if (matClass == 1) {
-        if (threads == 128 && slots == 4) TWL_OCC(128, 1, 4); else if (threads == 512 && slots == 1) TWL_OCC(512, 1, 1); else if (threads == 512 && slots == 2) TWL_OCC(512, 1, 2);
+#define TWL_OCC(NT_, MC_, KS_, SC_) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, talcoWavefrontKernel<NT_, MC_, KS_, SC_>, NT_, 0)
+    if (matClass < 0) {
+        if (threads == 128 && slots == 4) TWL_OCC(128, 0, 4, 1); else if (threads == 512 && slots == 2) TWL_OCC(512, 0, 2, 1);
+    } else if (matClass == 1) {
+        if (threads == 128 && slots == 4) TWL_OCC(128, 1, 4, 0); else if (threads == 512 && slots == 1) TWL_OCC(512, 1, 1, 0); else if (threads == 512 && slots == 2) TWL_OCC(512, 1, 2, 0);
     } else {
-        if (threads == 128 && slots == 4) TWL_OCC(128, 0, 4); else if (threads == 512 && slots == 1) TWL_OCC(512, 0, 1); else if (threads == 512 && slots == 2) TWL_OCC(512, 0, 2);
+        if (threads == 128 && slots == 4) TWL_OCC(128, 0, 4, 0); else if (threads == 512 && slots == 1) TWL_OCC(512, 0, 1, 0); else if (threads == 512 && slots == 2) TWL_OCC(512, 0, 2, 0);
     }
 #undef TWL_OCC
     return n;

@@ -22,6 +22,9 @@ int nucleotideMatrixClass(const float *score5x5);
 cudaError_t launchTalcoWavefront(int threads, int slots, int matClass, const TalcoArgs &args, int grid, cudaStream_t stream);
 cudaError_t launchCoRunGate(const int *arrived, int want, cudaStream_t stream);
 int wavefrontMaxCtasPerSm(int threads, int slots, int matClass);
+int simMatrixTiles(int refLen, int qryLen);
+cudaError_t launchSimMatrixAa(const float *prof, const DevPair *pairs, const int *order, int nOrder, const DevSim *simInfo, float *sim, const float *score,
+                              int maxTiles, cudaStream_t stream);
 cudaError_t launchDivSelfTest(const float *num, const float *den, int n, int *mismatches, cudaStream_t stream);
 } // namespace twl
 
@@ -133,7 +136,7 @@ void twl_destroy(twl_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ctx->dScore.release(); ctx->dProf.release(); ctx->dPairs.release(); ctx->dResults.release(); ctx->dPaths.release();
-    ctx->dOrder.release(); ctx->dOverflow.release(); ctx->dCounters.release(); ctx->dTb.release(); ctx->dState.release();
+    ctx->dOrder.release(); ctx->dOverflow.release(); ctx->dCounters.release(); ctx->dTb.release(); ctx->dState.release(); ctx->dSim.release(); ctx->dSimInfo.release();
     ctx->hProf.release(); ctx->hPaths.release(); ctx->hResults.release(); ctx->hWatchdog.release();
     if (ctx->evStart) cudaEventDestroy(ctx->evStart);
     if (ctx->evStop) cudaEventDestroy(ctx->evStop);
@@ -264,17 +267,43 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
     const int wideCap = std::max(wideCapIn, 8);                     // widest band any pair of the batch may legally reach
     const bool nucleotide = (ctx->P == 6) && !ctx->forceGeneric;
     struct Stage { int kind; int threads; int cap; int grid; size_t tbStride; int slots; };   // kind 0 wavefront (CTA per pair), 1 generic smem, 2 generic global, 3 warp per pair
-    const int matClass = nucleotide ? twl::nucleotideMatrixClass(ctx->hScore.data()) : 0;
+    // Protein: similarity matrices first (talco_sim.cu), then the same register-resident wavefront stages reading them (matClass -1),
+    // when the callers left the length bounds and the matrices fit the budget; otherwise the generic kernel scores on the fly.
+    bool proteinSim = (ctx->P == 22) && ctx->proteinSim && !ctx->forceGeneric && static_cast<int>(ctx->hChainOrder.size()) == n && n > 0;
+    int simMaxTiles = 0;
+    if (proteinSim) {
+        constexpr size_t kPad = 1024 + 16;                         // widest wavefront window + slack, in elements (even)
+        size_t cur = 0;
+        ctx->hSimInfo.assign(ctx->hSimRefUb.size(), twl::DevSim{0, 0, 0, 0});
+        for (int x : ctx->hChainOrder) {
+            if (x < 0 || x >= static_cast<int>(ctx->hSimRefUb.size()) || x >= static_cast<int>(ctx->hSimQryUb.size())) { proteinSim = false; break; }
+            const size_t refUb = static_cast<size_t>(std::max(ctx->hSimRefUb[x], 1)), qryUb = static_cast<size_t>(std::max(ctx->hSimQryUb[x], 1));
+            twl::DevSim &si = ctx->hSimInfo[x];
+            si.stride = static_cast<int>((qryUb + 3) & ~static_cast<size_t>(3));
+            si.gapOff = static_cast<long long>(cur + 2 * kPad);
+            cur += 2 * (kPad + ((refUb + 1) & ~static_cast<size_t>(1)) + 16);
+            si.simOff = static_cast<long long>(cur);
+            cur += (refUb + qryUb) * static_cast<size_t>(si.stride) + kPad;
+            simMaxTiles = std::max(simMaxTiles, twl::simMatrixTiles(static_cast<int>(refUb), static_cast<int>(qryUb)));
+            if (cur * sizeof(float) > ctx->simBudgetBytes) { proteinSim = false; break; }
+        }
+        if (proteinSim) {
+            TWL_CUDA(ctx, ctx->dSim.reserve(cur + 16));
+            TWL_CUDA(ctx, ctx->dSimInfo.reserve(ctx->hSimInfo.size()));
+            TWL_CUDA(ctx, cudaMemcpyAsync(ctx->dSimInfo.ptr, ctx->hSimInfo.data(), sizeof(twl::DevSim) * ctx->hSimInfo.size(), cudaMemcpyHostToDevice, ctx->stream));
+        }
+    }
+    const int matClass = nucleotide ? twl::nucleotideMatrixClass(ctx->hScore.data()) : (proteinSim ? -1 : 0);
     std::vector<Stage> stages;
     auto tbRows = [&](int w) { return (static_cast<size_t>(marker + 1) * w + 255) & ~static_cast<size_t>(255); };
-    if (nucleotide) {
+    if (nucleotide || proteinSim) {
         // few pairs (every CTA has an SM to itself): 512 threads x 2 rows, one 1024-row window for any legal nucleotide band
         // (latency_shape 3: 512 x 1 first, 512 x 2 for pairs whose band outgrows 512 rows); otherwise 128 threads x 4 rows,
         // 5 CTAs per SM, with 512 x 2 as the wide stage
         const bool lowLatency = ctx->latencyMode != 0 && (ctx->latencyMode == 1 || n <= ctx->smCount);
         int plan[3][2] = {{128, 4}, {512, 2}, {0, 0}};
         if (lowLatency) {
-            if (ctx->latencyShape == 3) { plan[0][0] = 512; plan[0][1] = 1; }
+            if (ctx->latencyShape == 3 && nucleotide) { plan[0][0] = 512; plan[0][1] = 1; }
             else { plan[0][0] = 512; plan[0][1] = 2; plan[1][0] = 0; }
         }
         for (int s = 0; s < 3 && plan[s][0]; ++s) {
@@ -345,6 +374,11 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
     a.score = ctx->dScore.ptr;
     if (ctx->P == 6) std::memcpy(a.scoreNt, ctx->hScore.data(), sizeof(a.scoreNt));
     a.tbScratch = ctx->dTb.ptr;
+    if (proteinSim) {
+        a.sim = ctx->dSim.ptr; a.simInfo = ctx->dSimInfo.ptr;
+        TWL_CUDA(ctx, twl::launchSimMatrixAa(a.prof, a.pairs, ctx->dOrder.ptr, n, a.simInfo, ctx->dSim.ptr, a.score, simMaxTiles, ctx->stream));
+        ctx->lastLaunches += (n + 65534) / 65535;
+    }
     for (int s = 0; s < nStages; ++s) {
         const Stage &st = stages[s];
         const bool hasNext = (s + 1 < nStages);
@@ -462,6 +496,11 @@ int twl_batch_run(twl_ctx *ctx) {
     ctx->timingPending = false;
     if (ctx->nPairs == 0) { ctx->ran = true; return TWL_OK; }
     TWL_CUDA(ctx, cudaEventRecord(ctx->evStart, ctx->stream));
+    if (ctx->P == 22) {   // protein path: exact lengths are known here
+        ctx->hSimRefUb.resize(ctx->nPairs); ctx->hSimQryUb.resize(ctx->nPairs);
+        for (int p = 0; p < ctx->nPairs; ++p) { ctx->hSimRefUb[p] = ctx->hPairs[p].refLen; ctx->hSimQryUb[p] = ctx->hPairs[p].qryLen; }
+        ctx->hChainOrder = ctx->hOrder;
+    }
     const int rc = twlLaunchDpChain(ctx, ctx->nPairs, ctx->maxFLen);
     if (rc != TWL_OK) return rc;
     TWL_CUDA(ctx, cudaEventRecord(ctx->evStop, ctx->stream));
@@ -515,6 +554,8 @@ int twl_set_option(twl_ctx *ctx, const char *name, int value) {
     if (std::strcmp(name, "inject_nomem") == 0) { ctx->injectNomem = std::max(0, value); return TWL_OK; }
     if (std::strcmp(name, "max_ctas_per_sm") == 0) { ctx->maxCtasPerSm = std::max(0, value); return TWL_OK; }   // occupancy experiments (0 = what fits)
     if (std::strcmp(name, "latency_shape") == 0) { if (value != 2 && value != 3) return TWL_E_ARG; ctx->latencyShape = value; return TWL_OK; }   // 2: 512x2, 3: 512x1 then 512x2
+    if (std::strcmp(name, "protein_sim") == 0) { ctx->proteinSim = value; return TWL_OK; }       // 0: proteins on the generic kernel only
+    if (std::strcmp(name, "sim_budget_mb") == 0) { ctx->simBudgetBytes = static_cast<size_t>(std::max(1, value)) << 20; return TWL_OK; }
     if (std::strcmp(name, "latency_mode") == 0) { ctx->latencyMode = value; return TWL_OK; }     // -1 auto, 0 off, 1 always
     return fail(ctx, TWL_E_ARG, std::string("twl_set_option: unknown option ") + name);
 }

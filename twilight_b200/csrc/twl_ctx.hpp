@@ -91,6 +91,14 @@ struct twl_ctx {
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
     int latencyShape = 2;        // 2: 512 threads x 2 rows; 3: 512 x 1 first, 512 x 2 for pairs whose band outgrows 512 rows
     bool forceGeneric = false;   // route nucleotide batches through the generic kernel (A/B parity + benchmarking)
+    // Protein path (talco_sim.cu + wavefront kernel with SC = 1): the callers of twlLaunchDpChain leave, per pair index, upper
+    // bounds of the two profile lengths and the host copy of the work list; the chain lays the similarity matrices out from those.
+    int proteinSim = 1;          // 0: proteins run on the generic kernel only (A/B)
+    size_t simBudgetBytes = static_cast<size_t>(16) << 30;   // larger batches fall back to the generic kernel
+    std::vector<int> hSimRefUb, hSimQryUb, hChainOrder;
+    std::vector<twl::DevSim> hSimInfo;
+    DevBuf<float> dSim;
+    DevBuf<twl::DevSim> dSimInfo;
     float lastMs = -1.0f;
     int lastLaunches = 0;
     bool timingPending = false;

@@ -54,6 +54,16 @@ struct DevResult {
     int resRefOff, resQryOff;       // with status kStatusRetryWide: where the failing tile starts; the next kernel of the chain resumes there
 };
 
+// Protein path: where a pair's similarity matrix and compact reference-side gap penalties live inside TalcoArgs::sim (offsets in
+// floats). Matrix cell (query row i, reference column j) is at simOff + (i + j) * stride + i; the (gapOpen, gapExtend) pair of
+// reference column j at gapOff + 2 * j. Both regions are padded so that the wavefront kernel's dead slots read inside the buffer.
+struct DevSim {
+    long long simOff;
+    long long gapOff;
+    int stride;
+    int pad;
+};
+
 struct TalcoArgs {
     const float *prof;
     const DevPair *pairs;
@@ -90,6 +100,8 @@ struct TalcoArgs {
     int *feedList;           // mode 2: entries appended by the producers (-1 until written)
     int *feedCount;          // mode 2: number of appended entries
     int *feedCursor;         // mode 2: next entry to take
+    const float *sim;        // protein path (talco_sim.cu): similarity matrices + gap arrays of the batch, see DevSim
+    const DevSim *simInfo;   // per pair
     unsigned long long *coTrace;   // diagnostics (nullable): per pair [4] = handed over, taken, finished (globaltimer ns), taker's role
 };
 

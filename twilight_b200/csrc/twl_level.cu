@@ -741,6 +741,11 @@ int runLevelChunkImpl(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pair
     while (!work.empty()) {
         const int nw = static_cast<int>(work.size());
         TWL_CUDA(ctx, cudaMemcpyAsync(ctx->dOrder.ptr, work.data(), sizeof(int) * nw, cudaMemcpyHostToDevice, ctx->stream));
+        if (P == 22) {   // protein path: profile lengths before gappy-column removal bound the similarity matrices
+            ctx->hSimRefUb.resize(n); ctx->hSimQryUb.resize(n);
+            for (int p = 0; p < n; ++p) { ctx->hSimRefUb[p] = pairs[begin + p].ref.aln_len; ctx->hSimQryUb[p] = pairs[begin + p].qry.aln_len; }
+            ctx->hChainOrder = work;
+        }
         int rc = twlLaunchDpChain(ctx, nw, maxF);
         if (rc != TWL_OK) return rc;
         if (first) TWL_CUDA(ctx, cudaEventRecord(L->ev[3], ctx->stream));
@@ -951,8 +956,10 @@ int twl_align_level(twl_ctx *ctx, const twl_level_pair *pairs, int n_pairs, int 
         int end = begin;
         size_t bytes = 0;
         while (end < n_pairs) {
-            const size_t need = (static_cast<size_t>(pairs[end].ref.aln_len) + pairs[end].qry.aln_len) * (ctx->P * 4 + (ctx->P + 2) * 4 + 16) +
-                                (static_cast<size_t>(pairs[end].ref.n_ids) + pairs[end].qry.n_ids) * 24;
+            size_t need = (static_cast<size_t>(pairs[end].ref.aln_len) + pairs[end].qry.aln_len) * (ctx->P * 4 + (ctx->P + 2) * 4 + 16) +
+                          (static_cast<size_t>(pairs[end].ref.n_ids) + pairs[end].qry.n_ids) * 24;
+            if (ctx->P == 22 && ctx->proteinSim)   // the pair's similarity matrix (anti-diagonal-major: (ref + qry) x qry floats)
+                need += (static_cast<size_t>(pairs[end].ref.aln_len) + pairs[end].qry.aln_len) * (static_cast<size_t>(pairs[end].qry.aln_len) + 4) * 4;
             if (end > begin && bytes + need > budget) break;
             bytes += need;
             ++end;
