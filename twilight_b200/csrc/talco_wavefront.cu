@@ -301,9 +301,10 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? (SC ? 1024 : 640) / NT : 1)) 
                         const bool diagIn = (i - 1 >= L2) && (i - 1 <= U2);
                         match[c] = diagIn ? __fadd_rn(diagH, num[c]) : negInf;
                     }
-                    // ... except on diagonal 0 and while the band touches the first row/column of the first tile
-                    // (TALCO-XDrop.cpp:369-371, 445-449)
-                    if (k == 0 || (tile == 0 && (L0 == 0 || U0 == k))) {
+                    // ... except on diagonal 0 and on the first row / column of the first tile (TALCO-XDrop.cpp:369-371, 445-449):
+                    // only the warp that holds row 0 or the cell of column 0 (row k) takes this path
+                    const bool edgeCell = (tile == 0) && (iBase == 0 || static_cast<unsigned>(k - iBase) < static_cast<unsigned>(kSlots));
+                    if (k == 0 || __any_sync(0xffffffffu, edgeCell)) {
 #pragma unroll
                         for (int c = 0; c < kSlots; ++c) {
                             const int i = iBase + c, j = k - i;
