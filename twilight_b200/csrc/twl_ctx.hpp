@@ -4,6 +4,7 @@
 #include "../../include/twilight_b200.h"
 #include "twl_device.cuh"
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -31,11 +32,15 @@ struct PinBuf {
     size_t cap = 0;
     cudaError_t reserve(size_t n) {
         if (n <= cap) return cudaSuccess;
+        const size_t had = cap;
         if (ptr) cudaFreeHost(ptr);
         ptr = nullptr;
         cap = 0;
-        size_t want = n + n / 4 + 256;
+        // pinning costs about a millisecond per MB: grow by doubling so that a buffer that keeps growing over the levels of a big
+        // tree (cached msaFreq staging) is re-pinned O(log) times
+        size_t want = std::max(n + n / 4 + 256, 2 * had);
         cudaError_t e = cudaMallocHost(&ptr, want * sizeof(T));
+        if (e != cudaSuccess && want > n) { cudaGetLastError(); want = n; e = cudaMallocHost(&ptr, want * sizeof(T)); }
         if (e == cudaSuccess) cap = want;
         return e;
     }

@@ -15,8 +15,9 @@
 namespace {
 
 struct RowSlot {
-    char *buf[2] = {nullptr, nullptr};
-    int cap = 0, len = 0, storage = 0;
+    char *buf[2] = {nullptr, nullptr};   // alnStorage[2]; the buffer a level writes (the one that is not live) is allocated when first needed
+    int cap[2] = {0, 0};                 // and regrown on its own: a row that is never rewritten again never pays for a second buffer
+    int len = 0, storage = 0;
     float weight = 0.f;
     bool present = false;
 };
@@ -153,9 +154,18 @@ cudaError_t poolAlloc(TwlLevelState *L, size_t bytes, char **out) {
             ++L->poolNext;
             continue;
         }
-        const size_t sz = std::max(kPoolChunkBytes, bytes);
+        // chunks double the arena (up to 8 GB each): cudaMalloc costs milliseconds per CALL whatever the size (measured on the B200:
+        // 32 x 256 MB = 120-200 ms, 8 x 1 GB = 9 ms, 1 x 8 GB = 3 ms), and a 10^5-leaf run grows the arena to tens of GB
+        size_t have = 0;
+        for (size_t b : L->poolBytes) have += b;
+        size_t sz = std::max(bytes, std::min(std::max(kPoolChunkBytes, have), static_cast<size_t>(8) << 30));
         void *p = nullptr;
         cudaError_t e = cudaMalloc(&p, sz);
+        if (e == cudaErrorMemoryAllocation && sz > std::max(kPoolChunkBytes, bytes)) {   // not that much left: the smallest chunk that serves the request
+            cudaGetLastError();
+            sz = std::max(kPoolChunkBytes, bytes);
+            e = cudaMalloc(&p, sz);
+        }
         if (e != cudaSuccess) return e;
         L->pools.push_back(p);
         L->poolBytes.push_back(sz);
@@ -243,11 +253,10 @@ int twl_rows_upload(twl_ctx *ctx, int n, const int32_t *ids, const char *const *
         if (static_cast<size_t>(id) >= L->rows.size()) L->rows.resize(id + 1);
         RowSlot &r = L->rows[id];
         const int cap = std::max(16, 2 * lens[i]);                        // timesBigger = 2, sequencedb.cpp:40
-        if (!r.present || r.cap < lens[i]) {
-            if (r.present) { poolRecycle(L, r.buf[0], r.cap); poolRecycle(L, r.buf[1], r.cap); r.present = false; }
+        if (!r.present || r.cap[0] < lens[i]) {
+            if (r.present) { poolRecycle(L, r.buf[0], r.cap[0]); poolRecycle(L, r.buf[1], r.cap[1]); r.present = false; }
             TWL_CUDA(ctx, poolAlloc(L, cap, &r.buf[0]));
-            TWL_CUDA(ctx, poolAlloc(L, cap, &r.buf[1]));
-            r.cap = cap;
+            r.cap[0] = cap; r.buf[1] = nullptr; r.cap[1] = 0;               // the second buffer comes with the first level that rewrites the row
         }
         r.len = lens[i]; r.storage = 0; r.weight = weights[i]; r.present = true;
         list[i].dev = r.buf[0]; list[i].stageOff = static_cast<long long>(total); list[i].len = lens[i]; list[i].pad = 0;
@@ -319,11 +328,10 @@ int twl_rows_import(twl_ctx *ctx, int n, const int32_t *ids, const int32_t *lens
         if (static_cast<size_t>(id) >= L->rows.size()) L->rows.resize(id + 1);
         RowSlot &r = L->rows[id];
         const int cap = std::max(16, 2 * lens[i]);
-        if (!r.present || r.cap < lens[i]) {
-            if (r.present) { poolRecycle(L, r.buf[0], r.cap); poolRecycle(L, r.buf[1], r.cap); r.present = false; }
+        if (!r.present || r.cap[0] < lens[i]) {
+            if (r.present) { poolRecycle(L, r.buf[0], r.cap[0]); poolRecycle(L, r.buf[1], r.cap[1]); r.present = false; }
             TWL_CUDA(ctx, poolAlloc(L, cap, &r.buf[0]));
-            TWL_CUDA(ctx, poolAlloc(L, cap, &r.buf[1]));
-            r.cap = cap;
+            r.cap[0] = cap; r.buf[1] = nullptr; r.cap[1] = 0;               // the second buffer comes with the first level that rewrites the row
         }
         r.len = lens[i]; r.storage = 0; r.weight = weights[i]; r.present = true;
         list[i].dev = r.buf[0]; list[i].stageOff = static_cast<long long>(offsets[i]); list[i].len = lens[i]; list[i].pad = 0;
@@ -344,8 +352,8 @@ int twl_rows_drop(twl_ctx *ctx, int n, const int32_t *ids) {
     for (int i = 0; i < n; ++i) {
         if (ids[i] < 0 || static_cast<size_t>(ids[i]) >= L->rows.size() || !L->rows[ids[i]].present) continue;
         RowSlot &r = L->rows[ids[i]];
-        poolRecycle(L, r.buf[0], r.cap);       // everything that still reads the buffers is stream-ordered before their next use
-        poolRecycle(L, r.buf[1], r.cap);
+        poolRecycle(L, r.buf[0], r.cap[0]);    // everything that still reads the buffers is stream-ordered before their next use
+        poolRecycle(L, r.buf[1], r.cap[1]);
         r = RowSlot();
     }
     return TWL_OK;
@@ -398,11 +406,10 @@ int twl_rows_migrate(twl_ctx *src, twl_ctx *dst, int n, const int32_t *ids) {
         if (static_cast<size_t>(id) >= LD->rows.size()) LD->rows.resize(id + 1);
         RowSlot &r = LD->rows[id];
         const int cap = std::max(16, 2 * lens[i]);
-        if (!r.present || r.cap < lens[i]) {
-            if (r.present) { poolRecycle(LD, r.buf[0], r.cap); poolRecycle(LD, r.buf[1], r.cap); r.present = false; }
+        if (!r.present || r.cap[0] < lens[i]) {
+            if (r.present) { poolRecycle(LD, r.buf[0], r.cap[0]); poolRecycle(LD, r.buf[1], r.cap[1]); r.present = false; }
             TWL_CUDA(dst, poolAlloc(LD, cap, &r.buf[0]));
-            TWL_CUDA(dst, poolAlloc(LD, cap, &r.buf[1]));
-            r.cap = cap;
+            r.cap[0] = cap; r.buf[1] = nullptr; r.cap[1] = 0;
         }
         r.len = lens[i]; r.storage = 0; r.weight = weights[i]; r.present = true;
         list[i].dev = r.buf[0];
@@ -489,7 +496,7 @@ namespace {
 
 // What runLevelChunk changed in the row store before its kernels ran: restored when the chunk fails (a CUDA error, out of
 // memory), so that a caller who handles the error code still finds every row where it was.
-struct RowUndo { int id; char *buf[2]; int cap, storage, len; };
+struct RowUndo { int id; char *buf[2]; int cap[2], storage, len; };
 
 // TWL_TRACE=1: wall-clock of the host-side steps of a level chunk on stderr
 struct Trace {
@@ -590,6 +597,7 @@ int runLevelChunkImpl(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pair
         TWL_CUDA(ctx, ctx->dProf.reserve(profWords + 2 * kProfPadWords));
         if (ctx->dProf.cap != before) TWL_CUDA(ctx, cudaMemsetAsync(ctx->dProf.ptr, 0, ctx->dProf.cap * sizeof(float), ctx->stream));
     }
+    tr.mark("  reserve level scratch");
     TWL_CUDA(ctx, ctx->dPairs.reserve(n));
     TWL_CUDA(ctx, ctx->dResults.reserve(n));
     TWL_CUDA(ctx, ctx->dPaths.reserve(std::max<size_t>(pathBytes, 16)));
@@ -616,6 +624,7 @@ int runLevelChunkImpl(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pair
     TWL_CUDA(ctx, cudaMemcpyAsync(ctx->dPairs.ptr, dp.data(), sizeof(DevPair) * n, cudaMemcpyHostToDevice, ctx->stream));
     TWL_CUDA(ctx, cudaMemcpyAsync(ctx->dOrder.ptr, order.data(), sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
 
+    tr.mark("  H2D level description");
     // ---- the update list is laid out before anything runs, with every path sized by its upper bound (ref + qry columns),
     // so the whole level — profiles, DP, gappy-column restore, row rewrite — is enqueued without a host round trip
     std::vector<int> work;
@@ -623,7 +632,6 @@ int runLevelChunkImpl(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pair
     std::vector<DevUpdate> ups;
     std::vector<const char *> updIn;
     std::vector<char *> updOut;
-    std::vector<char> updRegrown;
     std::vector<int> updPair, upOfPair(n, -1);
     size_t chunkInts = 0, mergedWords = 0, finalBytes = 0;
     int maxUb = 0, maxRows = 1;
@@ -648,18 +656,15 @@ int runLevelChunkImpl(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pair
             const int cnt = (s == 0) ? u.nRef : u.nQry;
             for (int m = 0; m < cnt; ++m) {
                 RowSlot &r = L->rows[sd2[s]->seq_ids[m]];
-                journal.push_back({sd2[s]->seq_ids[m], {r.buf[0], r.buf[1]}, r.cap, r.storage, r.len});
+                journal.push_back({sd2[s]->seq_ids[m], {r.buf[0], r.buf[1]}, {r.cap[0], r.cap[1]}, r.storage, r.len});
                 updIn.push_back(r.buf[r.storage]);
-                if (r.cap < ub) {                                            // SequenceInfo::memCheck, sequencedb.cpp:57-76
-                    const int cap = 2 * ub;
-                    char *a0, *a1;
-                    TWL_CUDA(ctx, poolAlloc(L, cap, &a0));
-                    TWL_CUDA(ctx, poolAlloc(L, cap, &a1));
-                    // the live buffer keeps being read from its old place for this update; the new pair is used from now on
-                    r.buf[0] = a0; r.buf[1] = a1; r.cap = cap;
-                    updRegrown.push_back(1);
-                } else updRegrown.push_back(0);
-                updOut.push_back(r.buf[1 - r.storage]);
+                const int t = 1 - r.storage;                                 // the buffer this level writes
+                if (r.cap[t] < ub) {                                         // SequenceInfo::memCheck, sequencedb.cpp:57-76 (timesBigger = 2)
+                    char *fresh;
+                    TWL_CUDA(ctx, poolAlloc(L, 2 * static_cast<size_t>(ub), &fresh));
+                    r.buf[t] = fresh; r.cap[t] = 2 * ub;                     // the buffer it replaces (if any) is recycled once the level has succeeded
+                }
+                updOut.push_back(r.buf[t]);
                 r.storage = 1 - r.storage;                                   // changeStorage(); undone below if the pair fails
             }
         }
@@ -679,12 +684,14 @@ int runLevelChunkImpl(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pair
         updPair.push_back(p);
     }
     const int nu = static_cast<int>(ups.size());
+    tr.mark("  update list + row buffers");
     TWL_CUDA(ctx, L->hRes.reserve(n));
     TWL_CUDA(ctx, L->hUps.reserve(std::max(nu, 1)));
     TWL_CUDA(ctx, L->hNeed.reserve(2 * static_cast<size_t>(std::max(nu, 1))));
     TWL_CUDA(ctx, L->hSides.reserve(nSides));
     TWL_CUDA(ctx, L->hFreqPin.reserve(std::max<size_t>(freqWords, 1)));
     TWL_CUDA(ctx, L->hMergedPin.reserve(std::max<size_t>(mergedWords, 1)));
+    tr.mark("  reserve pinned");
     if (nu) {
         TWL_CUDA(ctx, L->dUps.reserve(nu));
         TWL_CUDA(ctx, L->dUpdPair.reserve(nu));
@@ -883,8 +890,7 @@ int runLevelChunkImpl(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pair
             for (int m = 0; m < cnt; ++m, ++at) {
                 RowSlot &r = L->rows[sd2[s]->seq_ids[m]];
                 if (out.status == 0) { r.len = u.pathLen; continue; }
-                r.storage = 1 - r.storage;                                   // the pair failed: the row keeps its old content
-                if (updRegrown[at]) TWL_CUDA(ctx, cudaMemcpyAsync(r.buf[r.storage], updIn[at], r.len, cudaMemcpyDeviceToDevice, ctx->stream));
+                r.storage = 1 - r.storage;                                   // the pair failed: the row keeps its old content (the live buffer was not touched)
             }
         }
         if (out.status != 0) continue;
@@ -975,7 +981,7 @@ int twl_align_level(twl_ctx *ctx, const twl_level_pair *pairs, int n_pairs, int 
             cudaStreamSynchronize(ctx->stream);
             for (auto it = journal.rbegin(); it != journal.rend(); ++it) {
                 RowSlot &r = L->rows[it->id];
-                r.buf[0] = it->buf[0]; r.buf[1] = it->buf[1]; r.cap = it->cap; r.storage = it->storage; r.len = it->len;
+                r.buf[0] = it->buf[0]; r.buf[1] = it->buf[1]; r.cap[0] = it->cap[0]; r.cap[1] = it->cap[1]; r.storage = it->storage; r.len = it->len;
             }
             cudaGetLastError();
             ctx->error = why;
@@ -987,7 +993,8 @@ int twl_align_level(twl_ctx *ctx, const twl_level_pair *pairs, int n_pairs, int 
     // buffers that regrown rows left behind serve other rows from now on (everything that read them is stream-ordered before)
     for (const RowUndo &u : journal) {
         const RowSlot &r = L->rows[u.id];
-        if (r.buf[0] != u.buf[0] && r.buf[1] != u.buf[0]) { poolRecycle(L, u.buf[0], u.cap); poolRecycle(L, u.buf[1], u.cap); }
+        for (int b = 0; b < 2; ++b)
+            if (u.buf[b] && r.buf[0] != u.buf[b] && r.buf[1] != u.buf[b]) poolRecycle(L, u.buf[b], u.cap[b]);
     }
     L->lastChunks = chunkNo;
     float total = 0.f;
