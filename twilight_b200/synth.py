@@ -288,6 +288,7 @@ DATASETS = {
     "rna_3k": (3000, 1500, "rna", 0.30, 0.03, 0.0, 12),        # msaFreq caching + parking (>= 1000 sequences per node)
     "rna_10k": (10000, 1500, "rna", 0.30, 0.03, 0.0, 13),      # C3 rung 10^4
     "rna_100k": (100000, 1500, "rna", 0.30, 0.03, 0.0, 18),    # C3 rung 10^5 (bench only: the CPU reference needs ~20 minutes)
+    "rna_1m": (1000000, 1500, "rna", 0.30, 0.03, 0.0, 19),     # C3 itself: 10^6 leaves (no golden md5: the CPU reference would need hours; run with --check)
     "sars_64": (64, 29700, "dna", 0.002, 0.002, 0.0001, 14),   # C4 shape: 30 kb, near-identical, rare short indels
     "prot_2k": (2000, 400, "protein", 0.45, 0.02, 0.0, 15),    # C5 shape: 400 aa, BLOSUM62
     # 300 leaves of which 3 carry 15 % N (low quality, io.cpp:131-163: excluded, or deferred with --no-filtering), 3 are
