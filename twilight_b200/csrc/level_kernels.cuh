@@ -580,12 +580,24 @@ __device__ __forceinline__ int consensusAlignWarp(int lane, const char *s1, int 
 // finish the walk without writing (it only records the largest matrix and row it would need in `need`) and the pair is
 // redone by the LARGE = true instantiation, whose matrices live in a per-block slice of a global scratch buffer sized by
 // the host from `need`. Same code, same bits; only where the scratch is differs.
+// A consensus alignment the walk has put off: the walk reserves m + n bytes of the final path for it (an alignment of m against n
+// columns is at most that long), fills them with the skip code 3 and moves on; consensusJobsKernel aligns all put-off run pairs of the
+// level in parallel and writes the ops at the start of the reserved bytes; pathCompactKernel squeezes the skip codes out. The walk
+// itself never needs the alignment's result (it advances by m reference and n query columns whatever the alignment looks like), so
+// the only sequential part left per pair is a walk of ~100 cycles per run.
+struct RestoreJob {
+    long long outOff;       // into finalPaths
+    long long refOff, qryOff;   // into cons
+    int m, n;
+};
+constexpr int8_t kOpSkip = 3;
+
 template <bool LARGE>
 __global__ void __launch_bounds__(32) gappyRestoreKernel(DevUpdate *ups, const int *updPair, const int *which, int nu, const DevPair *pairs,
                                                          DevResult *results, const DevSide *sides, const int *runs, const char *cons, int8_t *pathsWo,
                                                          int8_t *finalPaths, const float *score, int M, int isProtein, const signed char *aaLut,
                                                          float gapOpen, float gapExtend, long long *need, char *largeScratch,
-                                                         long long largeCells, int largeCols) {
+                                                         long long largeCells, int largeCols, RestoreJob *jobs, int *jobCount, int jobCap) {
     constexpr int kTb = LARGE ? 16 : kRestoreTbCells, kRow = LARGE ? 4 : kRestoreRowCap;
     __shared__ int8_t sTb[kTb];
     __shared__ float sM[2 * kRow], sX[2 * kRow], sY[2 * kRow];
@@ -654,7 +666,7 @@ __global__ void __launch_bounds__(32) gappyRestoreKernel(DevUpdate *ups, const i
         stageOps(0);
         int w = 0, r = 0, q = 0, gr = 0, gq = 0, a = 0;
         int nextR = (nR > 0) ? sRunR[0] : -1, nextQ = (nQ > 0) ? sRunQ[0] : -1;
-        bool giveUp = false;
+        bool giveUp = false, holed = false;
         for (;;) {
             // runs that start at the current original coordinates go in front of op a (helper.cpp:338-362)
             const bool hitR = (r == nextR), hitQ = (q == nextQ);
@@ -666,8 +678,26 @@ __global__ void __launch_bounds__(32) gappyRestoreKernel(DevUpdate *ups, const i
                     wantCells = max(wantCells, cells);
                     wantCols = max(wantCols, n + 1);
                 }
-                if (!giveUp) w += consensusAlignWarp(lane, consR + r, m, consQ + q, n, sScore, M, isProtein, aaLut, gapOpen, gapExtend, tb, dM, dX, dY,
-                                                     colCap, idx2, out + w);
+                if (!giveUp) {
+                    int slot = jobCap;
+                    if (!LARGE && jobs != nullptr) {
+                        if (lane == 0) slot = atomicAdd(jobCount, 1);
+                        slot = __shfl_sync(0xffffffffu, slot, 0);
+                    }
+                    if (slot < jobCap) {       // put off: reserve m + n bytes, aligned later by consensusJobsKernel
+                        if (lane == 0) {
+                            RestoreJob jb;
+                            jb.outOff = ups[k].pathOff + w; jb.refOff = sr.consOff + r; jb.qryOff = sq.consOff + q; jb.m = m; jb.n = n;
+                            jobs[slot] = jb;
+                        }
+                        for (int t = lane; t < m + n; t += 32) out[w + t] = kOpSkip;
+                        w += m + n;
+                        holed = true;
+                    } else {
+                        w += consensusAlignWarp(lane, consR + r, m, consQ + q, n, sScore, M, isProtein, aaLut, gapOpen, gapExtend, tb, dM, dX, dY,
+                                                colCap, idx2, out + w);
+                    }
+                }
                 r += m; q += n;
             } else {
                 if (hitR) {
@@ -711,10 +741,58 @@ __global__ void __launch_bounds__(32) gappyRestoreKernel(DevUpdate *ups, const i
         }
         __syncwarp();
         if (lane == 0) {
-            if (giveUp) { need[2 * k] = wantCells; need[2 * k + 1] = wantCols; ups[k].pathLen = 0; }
-            else ups[k].pathLen = w;
+            if (giveUp) { need[2 * k] = wantCells; need[2 * k + 1] = wantCols; ups[k].pathLen = 0; ups[k].pad = 0; }
+            else { ups[k].pathLen = w; ups[k].pad = holed ? 1 : 0; }
         }
     }
+}
+
+// The consensus alignments the walks put off, one warp per job (same routine, same bits as the in-line path).
+__global__ void __launch_bounds__(32) consensusJobsKernel(const RestoreJob *jobs, const int *jobCount, int jobCap, const char *cons, int8_t *finalPaths,
+                                                          const float *score, int M, int isProtein, const signed char *aaLut, float gapOpen, float gapExtend) {
+    __shared__ int8_t sTb[kRestoreTbCells];
+    __shared__ float sM[2 * kRestoreRowCap], sX[2 * kRestoreRowCap], sY[2 * kRestoreRowCap];
+    __shared__ unsigned char sIdx2[kRestoreRowCap];
+    __shared__ float sScore[21 * 21];
+    const int lane = threadIdx.x;
+    for (int t = lane; t < M * M; t += 32) sScore[t] = score[t];
+    __syncwarp();
+    const int nJobs = min(*jobCount, jobCap);
+    for (int j = blockIdx.x; j < nJobs; j += gridDim.x) {
+        const RestoreJob jb = jobs[j];
+        consensusAlignWarp(lane, cons + jb.refOff, jb.m, cons + jb.qryOff, jb.n, sScore, M, isProtein, aaLut, gapOpen, gapExtend, sTb, sM, sX, sY,
+                           kRestoreRowCap, sIdx2, finalPaths + jb.outOff);
+        __syncwarp();
+    }
+}
+
+// Squeezes the skip codes out of the final paths that contain reserved bytes (DevUpdate::pad set by the walk), in place: one block per
+// pair walks the path in 1024-byte pieces; a piece is read completely before anything is written, and what is written lies at or before it.
+__global__ void __launch_bounds__(kLvlThreads) pathCompactKernel(DevUpdate *ups, int nu, int8_t *finalPaths) {
+    __shared__ int warpSums[kLvlThreads / 32];
+    const int k = blockIdx.x;
+    if (k >= nu || ups[k].pad == 0) return;
+    int8_t *path = finalPaths + ups[k].pathOff;
+    const int len = ups[k].pathLen;
+    int base = 0;
+    for (int c0 = 0; c0 < len; c0 += 4 * kLvlThreads) {
+        const int at = c0 + 4 * threadIdx.x;
+        int8_t v[4];
+        int keep = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            v[e] = (at + e < len) ? path[at + e] : kOpSkip;
+            keep += (v[e] != kOpSkip);
+        }
+        int total;
+        int dst = base + blockExclusiveScan(keep, warpSums, &total);      // barriers inside: every thread has read its bytes before any write below
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (v[e] != kOpSkip) path[dst++] = v[e];
+        base += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { ups[k].pathLen = base; ups[k].pad = 0; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -56,6 +56,8 @@ struct TwlLevelState {
     DevBuf<int> dUpdPair, dWhich;
     DevBuf<long long> dNeed;
     DevBuf<char> dLargeScratch;
+    DevBuf<twl::RestoreJob> dJobs;        // consensus alignments put off by the restore walks of a level chunk (level_kernels.cuh)
+    DevBuf<int> dJobCount;
     DevBuf<const char *> dUpdIn;
     PinBuf<twl::DevResult> hRes;
     PinBuf<twl::DevUpdate> hUps;
@@ -214,7 +216,7 @@ void twlLevelDestroy(twl_ctx *ctx) {
     L->dMerged.release(); L->dCons.release(); L->dGap.release(); L->dRuns.release(); L->dChunkCounts.release(); L->dUps.release();
     L->dFinalPaths.release(); L->dAaLut.release(); L->dCopies.release(); L->dStage.release(); L->hStage.release();
     L->hRes.release(); L->hUps.release(); L->hNeed.release(); L->hFinal.release(); L->hSides.release(); L->hFreqPin.release(); L->hMergedPin.release();
-    L->dUps2.release(); L->dUpdPair.release(); L->dNeed.release(); L->dWhich.release(); L->dLargeScratch.release(); L->dUpdIn.release();
+    L->dUps2.release(); L->dUpdPair.release(); L->dNeed.release(); L->dWhich.release(); L->dLargeScratch.release(); L->dUpdIn.release(); L->dJobs.release(); L->dJobCount.release();
     for (auto &e : L->ev) if (e) cudaEventDestroy(e);
     for (auto &e : L->sliceEv) cudaEventDestroy(e);
     if (L->stageFree) cudaEventDestroy(L->stageFree);
@@ -792,11 +794,25 @@ int runLevelChunkImpl(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pair
         return TWL_OK;
     };
     if (nu) {
+        // walk (one warp per pair, consensus alignments of coinciding runs put off) -> all put-off alignments in parallel -> compaction
+        static const int jobCap = [] { const char *e = std::getenv("TWL_RESTORE_JOBS"); return e ? std::max(0, std::atoi(e)) : (1 << 20); }();   // 0: align in line (A/B)
+        TWL_CUDA(ctx, L->dJobs.reserve(std::max(jobCap, 1)));
+        TWL_CUDA(ctx, L->dJobCount.reserve(1));
+        TWL_CUDA(ctx, cudaMemsetAsync(L->dJobCount.ptr, 0, sizeof(int), ctx->stream));
         gappyRestoreKernel<false><<<std::min(nu, ctx->smCount * 32), 32, 0, ctx->stream>>>(
             L->dUps.ptr, L->dUpdPair.ptr, nullptr, nu, ctx->dPairs.ptr, ctx->dResults.ptr, L->dSides.ptr, L->dRuns.ptr, L->dCons.ptr, ctx->dPaths.ptr,
-            L->dFinalPaths.ptr, ctx->dScore.ptr, ctx->M, P == 6 ? 0 : 1, L->dAaLut.ptr, ctx->gapOpen, ctx->gapExtend, L->dNeed.ptr, nullptr, 0, 0);
+            L->dFinalPaths.ptr, ctx->dScore.ptr, ctx->M, P == 6 ? 0 : 1, L->dAaLut.ptr, ctx->gapOpen, ctx->gapExtend, L->dNeed.ptr, nullptr, 0, 0,
+            jobCap ? L->dJobs.ptr : nullptr, L->dJobCount.ptr, jobCap);
         TWL_CUDA(ctx, cudaGetLastError());
         ctx->lastLaunches += 1;
+        if (jobCap) {
+            consensusJobsKernel<<<ctx->smCount * 8, 32, 0, ctx->stream>>>(L->dJobs.ptr, L->dJobCount.ptr, jobCap, L->dCons.ptr, L->dFinalPaths.ptr, ctx->dScore.ptr,
+                                                                     ctx->M, P == 6 ? 0 : 1, L->dAaLut.ptr, ctx->gapOpen, ctx->gapExtend);
+            TWL_CUDA(ctx, cudaGetLastError());
+            pathCompactKernel<<<nu, kLvlThreads, 0, ctx->stream>>>(L->dUps.ptr, nu, L->dFinalPaths.ptr);
+            TWL_CUDA(ctx, cudaGetLastError());
+            ctx->lastLaunches += 2;
+        }
         TWL_CUDA(ctx, cudaEventRecord(L->ev[6], ctx->stream));
         const int rc = launchUpdate(L->dUps.ptr, nu, maxUb, maxRows);
         if (rc != TWL_OK) return rc;
@@ -840,7 +856,7 @@ int runLevelChunkImpl(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pair
         gappyRestoreKernel<true><<<blocks, 32, 0, ctx->stream>>>(
             L->dUps.ptr, L->dUpdPair.ptr, L->dWhich.ptr, nr, ctx->dPairs.ptr, ctx->dResults.ptr, L->dSides.ptr, L->dRuns.ptr, L->dCons.ptr, ctx->dPaths.ptr,
             L->dFinalPaths.ptr, ctx->dScore.ptr, ctx->M, P == 6 ? 0 : 1, L->dAaLut.ptr, ctx->gapOpen, ctx->gapExtend, L->dNeed.ptr, L->dLargeScratch.ptr,
-            wantCells, static_cast<int>(wantCols));
+            wantCells, static_cast<int>(wantCols), nullptr, nullptr, 0);
         TWL_CUDA(ctx, cudaGetLastError());
         ctx->lastLaunches += 1;
         TWL_CUDA(ctx, cudaMemcpyAsync(L->hUps.ptr, L->dUps.ptr, sizeof(DevUpdate) * nu, cudaMemcpyDeviceToHost, ctx->stream));
