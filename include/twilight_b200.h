@@ -194,9 +194,14 @@ int twl_last_launch_count(const twl_ctx *ctx);
  * (default 8; 0 = run the wide-band kernel after the narrow one instead of beside it), "latency_mode" (-1 auto, 0 off,
  * 1 always: the one-CTA-per-SM shape for levels with few pairs), "latency_shape" (2 = 512 threads x 2 rows, default;
  * 3 = 512 x 1 first and 512 x 2 for pairs whose band outgrows 512 rows), "max_ctas_per_sm" (occupancy experiments),
+ * "protein_sim" (1 default: proteins compute every pair's similarity matrix with a dependency-free kernel and run the recurrence
+ * on the register-resident wavefront kernel; 0 = the generic kernel scores on the fly), "sim_budget_mb" (default 16384: a chain
+ * whose matrices need more falls back to the generic kernel),
  * "dp_trace" = 1 prints per-stage times to stderr. "inject_nomem" = n makes the n-th following twl_align_level call fail with
  * TWL_E_NOMEM after its kernels ran (tests of the all-or-nothing rollback and of the adapter's spill-and-retry path).
- * The environment variable TWL_OPTIONS="name=value,name=value" applies the same switches at twl_init. */
+ * The environment variable TWL_OPTIONS="name=value,name=value" applies the same switches at twl_init. Environment only:
+ * TWL_RESTORE_JOBS=0 aligns coinciding gappy runs in line during the restore walk instead of putting them off to the parallel job
+ * kernel (A/B); TWL_LEVEL_BUDGET_MB caps the scratch of a level chunk; TWL_TRACE=1 prints the host-side steps of every level chunk. */
 int twl_set_option(twl_ctx *ctx, const char *name, int value);
 
 /* Device self-test: evaluates the reciprocal-based exact division used by the DP kernels and the IEEE divide on n

@@ -129,13 +129,18 @@ def test_level_is_chunked_transparently(monkeypatch):
     assert st_b.launches > st_a.launches
 
 
+@pytest.mark.parametrize("jobs", [None, "0", "1"])
 @pytest.mark.parametrize("ins_len,expect_large", [(25, 0), (150, 1), (1300, 1)])
-def test_coinciding_gappy_runs_are_realigned(ins_len, expect_large):
+def test_coinciding_gappy_runs_are_realigned(ins_len, expect_large, jobs, monkeypatch):
     """Removed runs of both nodes that start at the same path position are aligned against each other (pairwiseGlobal,
     alignment-helper.cpp:243-322): in the restore kernel's shared memory when small, by a second pass of the same kernel
     with global scratch when the matrix exceeds it (150: by cells; 1300: also by row length). Same final path and rows as
     the oracle either way."""
     import twilight_b200
+    # jobs: default = consensus alignments put off to the parallel job kernel + compaction; "0" = aligned in line by the walk;
+    # "1" = a job list of one entry (the rest in line: the list-full path)
+    if jobs is not None:
+        monkeypatch.setenv("TWL_RESTORE_JOBS", jobs)
     rng = np.random.default_rng(5)
     letters = np.frombuffer(b"ACGU", np.uint8)
     anc = rng.choice(letters, 500)

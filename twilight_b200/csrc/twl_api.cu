@@ -321,13 +321,17 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
     if (wideCap > stages.back().cap) stages.push_back({2, twl::genericThreads(), wideCap, std::min(n, ctx->smCount), tbBytesPerCta(marker), 0});
 
     // Co-run: stage 0 (narrow window, 5 CTAs per SM) and stage 1 (wide window) execute at the same time; see TalcoArgs::coMode.
+    // Only for levels of more than one wave of narrow CTAs (the regime it was built and measured for). With about one wave or less the
+    // wide workers could only ever serve handed-over pairs and the gain is a few ms per level at best (10^5-leaf run: five such levels,
+    // ~5 ms of wide stage each); those levels run the stages one after the other.
+    int perSm0 = (nucleotide && !stages.empty() && stages[0].kind == 0) ? std::max(1, twl::wavefrontMaxCtasPerSm(stages[0].threads, stages[0].slots, matClass)) : 1;
+    if (ctx->maxCtasPerSm > 0) perSm0 = std::min(perSm0, ctx->maxCtasPerSm);
     const bool coRun = nucleotide && ctx->wideWorkers > 0 && stages.size() >= 2 && stages[0].kind == 0 && stages[1].kind == 0 &&
-                       stages[1].cap > stages[0].cap && n > ctx->smCount;
+                       stages[1].cap > stages[0].cap && n > ctx->smCount * perSm0;
     int wideGrid = 0;
     bool takeMain = false;
     if (coRun) {
-        int perSm = std::max(1, twl::wavefrontMaxCtasPerSm(stages[0].threads, stages[0].slots, matClass));
-        if (ctx->maxCtasPerSm > 0) perSm = std::min(perSm, ctx->maxCtasPerSm);
+        const int perSm = perSm0;
         // Many pairs per narrow CTA slot: a few wide workers that also eat from the main queue. About one wave or less: the
         // wide workers take the SMs the narrow kernel does not need and only serve handed-over pairs, which then restart at once.
         takeMain = n > ctx->smCount * perSm;
@@ -343,6 +347,28 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
             TWL_CUDA(ctx, cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming));
         }
     }
+    // TWL_TRACE: stage times of the PREVIOUS chain of this thread (its events have completed by now: a level ends with a synchronisation)
+    static const bool traceStages = std::getenv("TWL_TRACE") != nullptr;
+    thread_local std::vector<cudaEvent_t> stageEv;
+    thread_local int stageEvUsed = 0;
+    if (traceStages) {
+        if (stageEvUsed > 1) {
+            std::fprintf(stderr, "[twl]   previous dp chain, ms per stage:");
+            for (int e = 1; e < stageEvUsed; ++e) { float ms = 0.f; cudaEventElapsedTime(&ms, stageEv[e - 1], stageEv[e]); std::fprintf(stderr, " %.3f", ms); }
+            std::fprintf(stderr, "\n");
+        }
+        stageEvUsed = 0;
+    }
+    auto markStage = [&]() {
+        if (!traceStages) return;
+        if (stageEvUsed == static_cast<int>(stageEv.size())) { cudaEvent_t e; cudaEventCreate(&e); stageEv.push_back(e); }
+        cudaEventRecord(stageEv[stageEvUsed++], ctx->stream);
+    };
+    if (traceStages) {
+        std::fprintf(stderr, "[twl]   dp chain: %d pairs, co-run %d, stages", n, coRun ? 1 : 0);
+        for (const Stage &st : stages) std::fprintf(stderr, " [kind %d %dx%d cap %d grid %d]", st.kind, st.threads, st.slots, st.cap, st.grid);
+        std::fprintf(stderr, "\n");
+    }
     size_t tbBytes = 0, stateWords = 0;
     for (const Stage &st : stages) {
         tbBytes = std::max(tbBytes, st.tbStride * static_cast<size_t>(st.grid));
@@ -351,8 +377,19 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
     const size_t tbNarrow = coRun ? stages[0].tbStride * static_cast<size_t>(stages[0].grid) : 0;
     if (coRun) tbBytes = std::max({tbBytes, tbNarrow + stages[1].tbStride * static_cast<size_t>(stages[1].grid),
                                    stages[1].tbStride * static_cast<size_t>(std::min(n, ctx->smCount))});
-    TWL_CUDA(ctx, ctx->dTb.reserve(tbBytes));
-    if (stateWords) TWL_CUDA(ctx, ctx->dState.reserve(stateWords));
+    // Scratch is reserved for the largest plan a context of this alphabet can see, not for this chain: a buffer that regrows in the middle of
+    // a run costs a cudaFree + cudaMalloc, which now and then stall for 100-700 ms (measured: the level of a 10^5-leaf run at which the
+    // generic stage's band cap outgrew the 25 % slack of dState took 15 ms in most runs and up to 700 ms in others, tools/variance_levels.sh).
+    {
+        size_t tbCeil = static_cast<size_t>(ctx->smCount) * tbRows(1024);                                    // wide / low-latency wavefront, one CTA per SM
+        tbCeil = std::max(tbCeil, static_cast<size_t>(ctx->smCount) * kNarrowCtasPerSm * tbBytesPerCta(marker));   // generic kernels
+        if (nucleotide || proteinSim) {
+            const int perSmN = std::max(1, twl::wavefrontMaxCtasPerSm(128, 4, matClass));
+            tbCeil = std::max(tbCeil, static_cast<size_t>(ctx->smCount) * perSmN * tbRows(512) + static_cast<size_t>(ctx->smCount / 4) * tbRows(1024));   // narrow + co-running wide workers
+        }
+        TWL_CUDA(ctx, ctx->dTb.reserve(std::max(tbBytes, tbCeil)));
+        if (stateWords) TWL_CUDA(ctx, ctx->dState.reserve(std::max(stateWords, twl::genericStateWords(4096) * static_cast<size_t>(ctx->smCount))));
+    }
     const int nStages = static_cast<int>(stages.size());
     TWL_CUDA(ctx, ctx->dOverflow.reserve(static_cast<size_t>(n) * std::max(1, nStages - 1)));
 
@@ -379,6 +416,7 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
         TWL_CUDA(ctx, twl::launchSimMatrixAa(a.prof, a.pairs, ctx->dOrder.ptr, n, a.simInfo, ctx->dSim.ptr, a.score, simMaxTiles, ctx->stream));
         ctx->lastLaunches += (n + 65534) / 65535;
     }
+    markStage();
     for (int s = 0; s < nStages; ++s) {
         const Stage &st = stages[s];
         const bool hasNext = (s + 1 < nStages);
@@ -468,8 +506,9 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
         if (st.kind == 0) TWL_CUDA(ctx, twl::launchTalcoWavefront(st.threads, st.slots, matClass, a, st.grid, ctx->stream));
         else TWL_CUDA(ctx, twl::launchTalcoGeneric(ctx->P, st.kind == 2, a, st.grid, st.kind == 1 ? twl::genericStateWords(st.cap) * sizeof(float) : 0, ctx->stream));
         ctx->lastLaunches += 1;
+        markStage();
         if (ctx->dpTrace) {   // diagnosis only: serialises the chain and prints each stage's time and work count
-            static cudaEvent_t e0 = nullptr, e1 = nullptr;
+            thread_local cudaEvent_t e0 = nullptr, e1 = nullptr;   // one pair per host thread = per device (the adapter drives every device from its own thread)
             if (!e0) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
             if (s == 0) cudaEventRecord(e0, ctx->stream);   // includes nothing before the first launch's completion
             cudaEventRecord(e1, ctx->stream);

@@ -744,6 +744,7 @@ int runLevelChunkImpl(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pair
     TWL_CUDA(ctx, cudaEventRecord(L->ev[2], ctx->stream));
     ctx->lastLaunches += 2;
 
+    tr.mark("  launch profile kernels");
     // ---- phase 3: DP chain (pairs flagged profile-only are simply not listed). Task 0 reports failed pairs to the caller;
     // tasks 1 and 2 retry them with wider limits (alignment-cpu.cpp:116-129), which needs the statuses on the host.
     bool first = true;
@@ -777,6 +778,7 @@ int runLevelChunkImpl(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pair
         work.swap(again);
     }
     if (first) TWL_CUDA(ctx, cudaEventRecord(L->ev[3], ctx->stream));   // nothing to align in this chunk
+    tr.mark("  launch dp chain");
 
     // ---- phase 4: gappy columns back (helper.cpp:324-375), row rewrite + frequency merge (helper.cpp:377-448, 506-539)
     TWL_CUDA(ctx, cudaEventRecord(L->ev[5], ctx->stream));
@@ -795,7 +797,8 @@ int runLevelChunkImpl(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pair
     };
     if (nu) {
         // walk (one warp per pair, consensus alignments of coinciding runs put off) -> all put-off alignments in parallel -> compaction
-        static const int jobCap = [] { const char *e = std::getenv("TWL_RESTORE_JOBS"); return e ? std::max(0, std::atoi(e)) : (1 << 20); }();   // 0: align in line (A/B)
+        const char *jobEnv = std::getenv("TWL_RESTORE_JOBS");           // capacity of the job list; 0: align in line (A/B); a full list also aligns in line
+        const int jobCap = jobEnv ? std::max(0, std::atoi(jobEnv)) : (1 << 20);
         TWL_CUDA(ctx, L->dJobs.reserve(std::max(jobCap, 1)));
         TWL_CUDA(ctx, L->dJobCount.reserve(1));
         TWL_CUDA(ctx, cudaMemsetAsync(L->dJobCount.ptr, 0, sizeof(int), ctx->stream));
@@ -818,6 +821,7 @@ int runLevelChunkImpl(twl_ctx *ctx, TwlLevelState *L, const twl_level_pair *pair
         if (rc != TWL_OK) return rc;
     }
     TWL_CUDA(ctx, cudaEventRecord(L->ev[4], ctx->stream));
+    tr.mark("  launch restore + update");
 
     // ---- results back to the host: one synchronisation per chunk
     DevSide *hs = L->hSides.ptr;
