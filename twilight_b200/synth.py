@@ -290,7 +290,9 @@ DATASETS = {
     "rna_100k": (100000, 1500, "rna", 0.30, 0.03, 0.0, 18),    # C3 rung 10^5 (bench only: the CPU reference needs ~20 minutes)
     "rna_1m": (1000000, 1500, "rna", 0.30, 0.03, 0.0, 19),     # C3 itself: 10^6 leaves (no golden md5: the CPU reference would need hours; run with --check)
     "sars_64": (64, 29700, "dna", 0.002, 0.002, 0.0001, 14),   # C4 shape: 30 kb, near-identical, rare short indels
+    "sars_50k": (50000, 29700, "dna", 0.002, 0.002, 0.0001, 22),  # C4 itself: 5*10^4 genomes of 30 kb (no golden md5; run with --check)
     "prot_2k": (2000, 400, "protein", 0.45, 0.02, 0.0, 15),    # C5 shape: 400 aa, BLOSUM62
+    "prot_200k": (200000, 400, "protein", 0.45, 0.02, 0.0, 21),  # C5 itself: 2*10^5 proteins (no golden md5; run with --check)
     # 300 leaves of which 3 carry 15 % N (low quality, io.cpp:131-163: excluded, or deferred with --no-filtering), 3 are
     # unrelated random sequences and 2 are half-length fragments (pairs that fail the x-drop rule are deferred and
     # re-aligned with the widening ladder, alignment-cpu.cpp:108-129, progressive.cpp:275-298)
