@@ -21,5 +21,5 @@ done
 grep -h "twl-stats" $O/stderr.txt | tail -1 | cut -c1-700
 grep -h "Total Execution\|Alignment (length" $O/stdout.txt $O/stderr.txt | tail -3
 echo "check: $(grep -h 'Completed checking' $O/stderr.txt | awk '{s+=$3} END {print s}') sequences checked, $(grep -c 'did not match' $O/stdout.txt) complaints"
-ls -la /tmp/twl_ds/out.aln
+ls -la /tmp/twl_ds/out.aln; md5sum /tmp/twl_ds/out.aln
 rm -rf /tmp/twl_ds
