@@ -70,21 +70,23 @@ __device__ __forceinline__ void scoreDiagonal(const TalcoArgs &a, const float4 *
         // every thread: the four slots hit the four streams of the de-interleaved layout at float4 index m>>2 (or one less once
         // m-c crosses a multiple of 4). Columns outside [0, refLen) are only touched by slots that are not live; the profile
         // buffer is padded so the reads stay inside the allocation and their values are discarded.
+        // 32-bit index arithmetic (a side has far fewer than 2^31 float4): the stream part of the index is warp-uniform, the thread
+        // adds its own column group; one 64-bit multiply-add per load instead of a carry chain
         const int m = colBase - iBase;
         const int u = colBase & 3;
-        const float4 *pX = refX + (m >> 2);
-        const long long yOff = 4 * static_cast<long long>(refN4);
+        const int group = m >> 2;
+        const int yOff = 4 * refN4;
 #pragma unroll
         for (int c = 0; c < KS; ++c) {
-            long long at;
+            int at;
             if (KS == 4) {
                 const int stream = (u - c) & 3;
-                at = stream * refN4 - ((c > u) ? 1 : 0);
+                at = stream * refN4 - ((c > u) ? 1 : 0) + group;
             } else {
-                at = ntColIndex(m - c, refN4) - (m >> 2);   // rows per thread < 4: the stream differs between threads
+                at = static_cast<int>(ntColIndex(m - c, refN4));   // rows per thread < 4: the stream differs between threads
             }
-            const float4 x = __ldg(pX + at);
-            const float4 y = __ldg(pX + at + yOff);
+            const float4 x = __ldg(refX + at);
+            const float4 y = __ldg(refX + (at + yOff));
             r[c][0] = x.x; r[c][1] = x.y; r[c][2] = x.z; r[c][3] = x.w; r[c][4] = y.x; r[c][5] = y.y;
             gOpR[c] = y.z; gExR[c] = y.w;
             gapR = gapR || (y.y != 0.0f);

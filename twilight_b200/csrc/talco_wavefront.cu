@@ -30,9 +30,8 @@ namespace twl {
 
 
 struct WaveShared {
-    alignas(16) int redMax[2][32];   // per warp: max score as ordered int ...
-    alignas(16) int redLo[2][32];    // ... first live row ...
-    alignas(16) int redHi[2][32];    // ... last live row (separate words: no packing moves, one 128-bit load fetches four warps)
+    alignas(16) int red[4][4];       // per diagonal (ring of four): {max score as ordered int, first live row, last live row, -}, folded by the
+                                     // warps that hold a surviving cell with shared-memory atomics; after the barrier every thread reads one word
     float2 edge[2][32];         // per warp: H and I of the warp's last slot (row-neighbour of the next warp's first slot)
     unsigned convMask[3];
     int8_t ops[2 * kMaxMarker + 16];
@@ -159,6 +158,7 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? (SC ? 1024 : 640) / NT : 1)) 
             }
         }
         __syncthreads();   // every thread has read the previous result before thread 0 overwrites it at the end
+        const int4 redInit = make_int4(orderedInt(negInf), 0x7fffffff, -0x7fffffff, 0);
 
         while (!lastTile) {
             const int refLen = pr.refLen - refOff, qryLen = pr.qryLen - qryOff;
@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? (SC ? 1024 : 640) / NT : 1)) 
                 sCD[0][t] = sCD[1][t] = kDelBoundary;
             }
             if (tid < 3) sh.convMask[tid] = 3u;
+            if (tid >= 32 && tid < 36) *reinterpret_cast<int4 *>(sh.red[tid - 32]) = redInit;
             __syncthreads();
 
             // per-slot register state
@@ -395,30 +396,22 @@ __global__ void __launch_bounds__(NT, (NT <= 128 ? (SC ? 1024 : 640) / NT : 1)) 
                 }
 
                 // one barrier per diagonal: publish the warp's edge values and its reduction
-                const int wMax = __reduce_max_sync(0xffffffffu, orderedInt(myMax));
-                const int wLo = __reduce_min_sync(0xffffffffu, myLo);
                 const int wHi = __reduce_max_sync(0xffffffffu, myHi);
                 if (lane == 31) edgeOut[g0 * 32] = make_float2(h1[kSlots - 1], i1[kSlots - 1]);
-                if (lane == 0) { sh.redMax[g0][warp] = wMax; sh.redLo[g0][warp] = wLo; sh.redHi[g0][warp] = wHi; }
+                if (wHi >= 0) {                                        // the warp holds a cell that survived (warp-uniform)
+                    const int wMax = __reduce_max_sync(0xffffffffu, orderedInt(myMax));
+                    const int wLo = __reduce_min_sync(0xffffffffu, myLo);
+                    if (lane == 0) {
+                        int *r = sh.red[k & 3];
+                        atomicMax(r, wMax); atomicMin(r + 1, wLo); atomicMax(r + 2, wHi);
+                    }
+                }
+                if (tid == NT - 1) *reinterpret_cast<int4 *>(sh.red[(k + 2) & 3]) = redInit;   // last read after barrier k-2, next folded after barrier k+1
                 __syncthreads();
                 int oMax, newL, newU;
-                if (NW > 8) {           // many warps: one shared-memory read per lane and three warp reductions
-                    oMax = __reduce_max_sync(0xffffffffu, sh.redMax[g0][lane & (NW - 1)]);
-                    newL = __reduce_min_sync(0xffffffffu, sh.redLo[g0][lane & (NW - 1)]);
-                    newU = __reduce_max_sync(0xffffffffu, sh.redHi[g0][lane & (NW - 1)]);
-                } else if (NW == 4) {   // four warps: one 128-bit load per quantity
-                    const int4 m = *reinterpret_cast<const int4 *>(&sh.redMax[g0][0]);
-                    const int4 lo = *reinterpret_cast<const int4 *>(&sh.redLo[g0][0]);
-                    const int4 hi = *reinterpret_cast<const int4 *>(&sh.redHi[g0][0]);
-                    oMax = max(max(m.x, m.y), max(m.z, m.w));
-                    newL = min(min(lo.x, lo.y), min(lo.z, lo.w));
-                    newU = max(max(hi.x, hi.y), max(hi.z, hi.w));
-                } else {
-                    oMax = sh.redMax[g0][0]; newL = sh.redLo[g0][0]; newU = sh.redHi[g0][0];
-#pragma unroll
-                    for (int w = 1; w < NW; ++w) {
-                        oMax = max(oMax, sh.redMax[g0][w]); newL = min(newL, sh.redLo[g0][w]); newU = max(newU, sh.redHi[g0][w]);
-                    }
+                {
+                    const int4 r = *reinterpret_cast<const int4 *>(sh.red[k & 3]);
+                    oMax = r.x; newL = r.y; newU = r.z;
                 }
                 if (newL == 0x7fffffff) { newL = U0 + 1; newU = L0 - 1; }
                 maxScorePrime = fmaxf(maxScorePrime, orderedFloat(oMax));
