@@ -10,8 +10,8 @@
 // 32-byte reference column (two LDG.128 that hit L1; the lines needed a few diagonals ahead are prefetched) and one
 // traceback byte (the four slots of a thread store one coalesced 32-bit word). Row-neighbour values come from the
 // thread's own registers for slots 1..3 and from one warp shuffle for slot 0; warps exchange their edge values and the
-// per-diagonal reduction (running maximum for the X-drop rule, first / last live row) through shared memory with ONE
-// barrier per diagonal. The four cells of a thread are evaluated branch-free so that their dependent FP chains
+// per-diagonal reduction (running maximum for the X-drop rule, first / last live row: folded into one word per diagonal with
+// shared-memory atomics by the warps that hold a surviving cell) through shared memory with ONE barrier per diagonal. The four cells of a thread are evaluated branch-free so that their dependent FP chains
 // interleave; warps that hold no live cell skip the evaluation.
 //
 // What is kept bit-identical to the reference CPU path (src/TALCO-XDrop.cpp:233-689): the float operation order of
