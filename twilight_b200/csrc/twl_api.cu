@@ -509,14 +509,17 @@ int twlLaunchDpChain(twl_ctx *ctx, int n, int wideCapIn) {
         markStage();
         if (ctx->dpTrace) {   // diagnosis only: serialises the chain and prints each stage's time and work count
             thread_local cudaEvent_t e0 = nullptr, e1 = nullptr;   // one pair per host thread = per device (the adapter drives every device from its own thread)
+            thread_local bool e0Recorded = false;
             if (!e0) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
-            if (s == 0) cudaEventRecord(e0, ctx->stream);   // includes nothing before the first launch's completion
+            const bool firstReported = (s == 0) || !e0Recorded;     // the co-run branch above reports stages 0 + 1 itself and continues past this block
+            if (firstReported) { cudaEventRecord(e0, ctx->stream); e0Recorded = true; }   // includes nothing before the first launch's completion
             cudaEventRecord(e1, ctx->stream);
             cudaStreamSynchronize(ctx->stream);
             int host[16];
             cudaMemcpy(host, ctx->dCounters.ptr, sizeof(host), cudaMemcpyDeviceToHost);
             float ms = 0.f;
-            if (s > 0) cudaEventElapsedTime(&ms, e0, e1);
+            if (!firstReported) cudaEventElapsedTime(&ms, e0, e1);
+            if (s + 1 == nStages) e0Recorded = false;
             std::fprintf(stderr, "[twl dp] stage %d kind %d %dx%d grid %d: work %d, +%.3f ms since stage 0 ended\n", s, st.kind, st.threads, st.slots, st.grid,
                          host[2 * s + 1], ms);
         }
